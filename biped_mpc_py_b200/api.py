@@ -1,0 +1,345 @@
+"""Host-side mirror of the reference's MPC interface over the C ABI.
+
+* :class:`BatchedMPC` - N independent robots per call; device tensors in / device tensors out
+  (``step`` / ``solve`` / ``lowlevel`` / ``foot_positions``), or host numpy in / out through one
+  packed pinned staging buffer (``step_host`` / ``solve_host``) - the end-to-end path.
+* ``solve_mpc`` / ``lowLevelControl`` / ``getFootPositionWorld`` - the reference's own signatures
+  (MPC.py:187, 444, 406) for one robot, so the reference script's loop can swap them in.
+
+PyTorch is used only to own device / pinned memory and CUDA streams; every number is produced
+by the CUDA kernels in ``csrc/`` behind ``include/biped_mpc_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .gait import gait_phase
+from .params import MPC, Biped, pack_params, params_key
+
+STATUS_OPTIMAL, STATUS_MAXITER, STATUS_NUMERIC, STATUS_BADINPUT = 0, 1, 2, 3
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("biped_mpc_py_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _align(n: int, a: int = 16) -> int:
+    return (n + a - 1) // a * a
+
+
+class BatchedMPC:
+    """One solver handle: fixed parameters (``mpc``, ``biped``), one device, batches up to ``max_batch``."""
+
+    def __init__(self, mpc=None, biped=None, max_batch: int = 4096, device: int = 0, extend_gait: bool = False,
+                 max_iter: int = 0, mu_tol: float = 0.0, rd_tol: float = 0.0):
+        torch = _torch()
+        self.mpc = mpc if mpc is not None else MPC()
+        self.biped = biped if biped is not None else Biped()
+        self.h = int(self.mpc.h)
+        self.max_batch = int(max_batch)
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.extend_gait = bool(extend_gait)
+        self._lib = _lib.load()
+        self._params = pack_params(self.mpc, self.biped, extend_gait, max_iter, mu_tol, rd_tol)
+        handle = ctypes.c_void_p()
+        _lib.check(self._lib.bmpc_create(ctypes.byref(self._params), self.device_index, self.max_batch,
+                                         ctypes.byref(handle)))
+        self._h = handle
+        h, nb = self.h, self.max_batch
+        f64, dev = torch.float64, self.device
+        # outputs are owned by the handle and reused every call (views are returned)
+        self.controls = torch.empty((nb, h, 12), dtype=f64, device=dev)
+        self.states = torch.empty((nb, h, 13), dtype=f64, device=dev)
+        self.tau = torch.empty((nb, 10), dtype=f64, device=dev)
+        self.status = torch.empty((nb,), dtype=torch.int32, device=dev)
+        self.iters = torch.empty((nb,), dtype=torch.int32, device=dev)
+        self.fric_active = torch.empty((nb, h), dtype=torch.uint8, device=dev)
+        self.resid = torch.empty((nb, 2), dtype=f64, device=dev)
+        self._stage = None  # packed host/device staging, created on first *_host call
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bmpc_launch_count(self._h))
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, t, shape, dtype, name):
+        torch = _torch()
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise TypeError(f"{name}: expected a tensor on {self.device}")
+        if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous {dtype} of shape {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _stream_ptr(self, stream):
+        torch = _torch()
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    # ------------------------------------------------------------------ device API
+    def step(self, x_fb, phase_k, t_swing, foot, contact, q, qd, pf_w, want_states: bool = False, stream=None):
+        """solve_mpc + lowLevelControl for N robots (device tensors).  Returns a dict of views."""
+        torch = _torch()
+        n = int(x_fb.shape[0])
+        if n > self.max_batch:
+            raise ValueError("batch larger than max_batch")
+        f64, h = torch.float64, self.h
+        args = [self._check(x_fb, (n, 12), f64, "x_fb"), self._check(phase_k, (n,), torch.int32, "phase_k"),
+                self._check(t_swing, (n,), f64, "t_swing"), self._check(foot, (n, 6), f64, "foot"),
+                self._check(contact, (n, h, 2), torch.uint8, "contact"), self._check(q, (n, 10), f64, "q"),
+                self._check(qd, (n, 10), f64, "qd"), self._check(pf_w, (n, 6), f64, "pf_w")]
+        outs = [ctypes.c_void_p(self.controls.data_ptr()),
+                ctypes.c_void_p(self.states.data_ptr()) if want_states else ctypes.c_void_p(0),
+                ctypes.c_void_p(self.tau.data_ptr()), ctypes.c_void_p(self.status.data_ptr()),
+                ctypes.c_void_p(self.iters.data_ptr()), ctypes.c_void_p(self.fric_active.data_ptr()),
+                ctypes.c_void_p(self.resid.data_ptr())]
+        _lib.check(self._lib.bmpc_step(self._h, n, *args, *outs, self._stream_ptr(stream)))
+        return self._views(n, want_states, True)
+
+    def solve(self, x_fb, phase_k, foot, contact, want_states: bool = True, stream=None):
+        """solve_mpc only (MPC.py:187-304) for N robots (device tensors)."""
+        torch = _torch()
+        n = int(x_fb.shape[0])
+        f64, h = torch.float64, self.h
+        args = [self._check(x_fb, (n, 12), f64, "x_fb"), self._check(phase_k, (n,), torch.int32, "phase_k"),
+                self._check(foot, (n, 6), f64, "foot"), self._check(contact, (n, h, 2), torch.uint8, "contact")]
+        outs = [ctypes.c_void_p(self.controls.data_ptr()),
+                ctypes.c_void_p(self.states.data_ptr()) if want_states else ctypes.c_void_p(0),
+                ctypes.c_void_p(self.status.data_ptr()), ctypes.c_void_p(self.iters.data_ptr()),
+                ctypes.c_void_p(self.fric_active.data_ptr()), ctypes.c_void_p(self.resid.data_ptr())]
+        _lib.check(self._lib.bmpc_solve(self._h, n, *args, *outs, self._stream_ptr(stream)))
+        return self._views(n, want_states, False)
+
+    def lowlevel(self, x_fb, t_swing, pf_w, q, qd, contact0, u0, stream=None):
+        """lowLevelControl only (MPC.py:444-470): u0 (N,12) -> tau (N,10)."""
+        torch = _torch()
+        n = int(x_fb.shape[0])
+        f64 = torch.float64
+        args = [self._check(x_fb, (n, 12), f64, "x_fb"), self._check(t_swing, (n,), f64, "t_swing"),
+                self._check(pf_w, (n, 6), f64, "pf_w"), self._check(q, (n, 10), f64, "q"),
+                self._check(qd, (n, 10), f64, "qd"), self._check(contact0, (n, 2), torch.uint8, "contact0"),
+                self._check(u0, (n, 12), f64, "u0")]
+        _lib.check(self._lib.bmpc_lowlevel(self._h, n, *args, ctypes.c_void_p(self.tau.data_ptr()),
+                                           self._stream_ptr(stream)))
+        return self.tau[:n]
+
+    def foot_positions(self, x_fb, q, out=None, stream=None):
+        """getFootPositionWorld (MPC.py:406-424) for N robots -> (N,6)."""
+        torch = _torch()
+        n = int(x_fb.shape[0])
+        f64 = torch.float64
+        if out is None:
+            out = torch.empty((n, 6), dtype=f64, device=self.device)
+        _lib.check(self._lib.bmpc_foot_positions(self._h, n, self._check(x_fb, (n, 12), f64, "x_fb"),
+                                                 self._check(q, (n, 10), f64, "q"),
+                                                 self._check(out, (n, 6), f64, "out"), self._stream_ptr(stream)))
+        return out
+
+    def debug_assemble(self, x_fb, phase_k, foot, contact):
+        """Reduced condensed QP (Hc, g) of ONE instance as numpy arrays (parity tests)."""
+        torch = _torch()
+        f64, h = torch.float64, self.h
+        nmax = 12 * h
+        H = torch.zeros((nmax, nmax), dtype=f64, device=self.device)
+        g = torch.zeros((nmax,), dtype=f64, device=self.device)
+        nn = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.bmpc_debug_assemble(
+            self._h, self._check(x_fb, (1, 12), f64, "x_fb"), self._check(phase_k, (1,), torch.int32, "phase_k"),
+            self._check(foot, (1, 6), f64, "foot"), self._check(contact, (1, h, 2), torch.uint8, "contact"),
+            ctypes.c_void_p(H.data_ptr()), ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(nn.data_ptr()),
+            self._stream_ptr(None)))
+        n = int(nn.item())
+        return H[:n, :n].cpu().numpy(), g[:n].cpu().numpy()
+
+    def _views(self, n, want_states, with_tau) -> Dict[str, object]:
+        out = dict(controls=self.controls[:n], status=self.status[:n], iters=self.iters[:n],
+                   fric_active=self.fric_active[:n], resid=self.resid[:n])
+        if want_states:
+            out["states"] = self.states[:n]
+        if with_tau:
+            out["tau"] = self.tau[:n]
+        return out
+
+    # ------------------------------------------------------------------ host (end-to-end) API
+    def _staging(self):
+        """One packed pinned host buffer + device mirror for inputs, one for outputs."""
+        if self._stage is not None:
+            return self._stage
+        torch = _torch()
+        nb, h = self.max_batch, self.h
+        in_bytes = _align(nb * 8 * (12 + 6 + 10 + 10 + 6 + 1)) + _align(nb * 4) + _align(nb * 2 * h) + 7 * 16
+        out_bytes = _align(nb * 8 * (12 * h + 13 * h + 10 + 2)) + 2 * _align(nb * 4) + _align(nb * h) + 7 * 16
+        st = dict(
+            h_in=torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True),
+            d_in=torch.empty(in_bytes, dtype=torch.uint8, device=self.device),
+            h_out=torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True),
+            d_out=torch.empty(out_bytes, dtype=torch.uint8, device=self.device),
+        )
+        st["h_in_np"] = st["h_in"].numpy()
+        st["h_out_np"] = st["h_out"].numpy()
+        self._stage = st
+        return st
+
+    @staticmethod
+    def _carve(sections):
+        """sections: list of (name, nbytes) -> dict name -> (offset, nbytes), 16-byte aligned."""
+        off, lay = 0, {}
+        for name, nbytes in sections:
+            lay[name] = (off, nbytes)
+            off = _align(off + nbytes)
+        return lay, off
+
+    def step_host(self, x_fb, t, foot, contact, q, qd, pf_w, phase_k=None, want_states: bool = False,
+                  lowlevel: bool = True):
+        """End-to-end tick with HOST numpy inputs and outputs (one H2D and one D2H copy).
+
+        ``t`` (N,) is the control time: ``phase_k`` defaults to ``int(t // dt) % h`` computed with the
+        reference's float expression (MPC.py:56,99) and ``t`` is also the swing-leg time (MPC.py:436).
+        Returns dict of numpy arrays: controls (N,h,12), tau (N,10), status, iters, fric_active, resid
+        and optionally states (N,h,13).  Synchronous.
+        """
+        torch = _torch()
+        x_fb = np.ascontiguousarray(x_fb, dtype=np.float64).reshape(-1, 12)
+        n, h = x_fb.shape[0], self.h
+        if n > self.max_batch:
+            raise ValueError("batch larger than max_batch")
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(n)
+        if phase_k is None:
+            period = 10 if self.extend_gait else h
+            phase_k = (gait_phase(t, self.mpc) % period)
+        st = self._staging()
+        ins = [("x_fb", x_fb), ("foot", np.asarray(foot, dtype=np.float64).reshape(n, 6))]
+        if lowlevel:
+            ins += [("q", np.asarray(q, dtype=np.float64).reshape(n, 10)),
+                    ("qd", np.asarray(qd, dtype=np.float64).reshape(n, 10)),
+                    ("pf_w", np.asarray(pf_w, dtype=np.float64).reshape(n, 6)), ("t", t)]
+        ins += [("phase_k", np.asarray(phase_k, dtype=np.int32).reshape(n)),
+                ("contact", np.asarray(contact, dtype=np.uint8).reshape(n, h, 2))]
+        lay_in, in_used = self._carve([(k, v.nbytes) for k, v in ins])
+        hin = st["h_in_np"]
+        for k, v in ins:
+            off, nb = lay_in[k]
+            hin[off:off + nb] = v.reshape(-1).view(np.uint8)
+        outs = [("controls", n * h * 12 * 8)]
+        if lowlevel:
+            outs.append(("tau", n * 10 * 8))
+        if want_states:
+            outs.append(("states", n * h * 13 * 8))
+        outs += [("resid", n * 2 * 8), ("status", n * 4), ("iters", n * 4), ("fric", n * h)]
+        lay_out, out_used = self._carve(outs)
+        stream = torch.cuda.current_stream(self.device)
+        st["d_in"][:in_used].copy_(st["h_in"][:in_used], non_blocking=True)
+        din, dout = st["d_in"].data_ptr(), st["d_out"].data_ptr()
+        P = lambda base, lay, k: ctypes.c_void_p(base + lay[k][0]) if k in lay else ctypes.c_void_p(0)
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        if lowlevel:
+            _lib.check(self._lib.bmpc_step(
+                self._h, n, P(din, lay_in, "x_fb"), P(din, lay_in, "phase_k"), P(din, lay_in, "t"),
+                P(din, lay_in, "foot"), P(din, lay_in, "contact"), P(din, lay_in, "q"), P(din, lay_in, "qd"),
+                P(din, lay_in, "pf_w"), P(dout, lay_out, "controls"), P(dout, lay_out, "states"),
+                P(dout, lay_out, "tau"), P(dout, lay_out, "status"), P(dout, lay_out, "iters"),
+                P(dout, lay_out, "fric"), P(dout, lay_out, "resid"), sp))
+        else:
+            _lib.check(self._lib.bmpc_solve(
+                self._h, n, P(din, lay_in, "x_fb"), P(din, lay_in, "phase_k"), P(din, lay_in, "foot"),
+                P(din, lay_in, "contact"), P(dout, lay_out, "controls"), P(dout, lay_out, "states"),
+                P(dout, lay_out, "status"), P(dout, lay_out, "iters"), P(dout, lay_out, "fric"),
+                P(dout, lay_out, "resid"), sp))
+        st["h_out"][:out_used].copy_(st["d_out"][:out_used], non_blocking=True)
+        stream.synchronize()
+        ho = st["h_out_np"]
+
+        def take(name, dtype, shape):
+            off, nb = lay_out[name]
+            return ho[off:off + nb].view(dtype).reshape(shape).copy()
+
+        res = dict(controls=take("controls", np.float64, (n, h, 12)), status=take("status", np.int32, (n,)),
+                   iters=take("iters", np.int32, (n,)), fric_active=take("fric", np.uint8, (n, h)),
+                   resid=take("resid", np.float64, (n, 2)))
+        if lowlevel:
+            res["tau"] = take("tau", np.float64, (n, 10))
+        if want_states:
+            res["states"] = take("states", np.float64, (n, h, 13))
+        self.last_h2d_bytes, self.last_d2h_bytes = int(in_used), int(out_used)
+        return res
+
+    def solve_host(self, x_fb, t, foot, contact, phase_k=None, want_states: bool = True):
+        """``solve_mpc`` only, host numpy in / out."""
+        return self.step_host(x_fb, t, foot, contact, None, None, None, phase_k=phase_k, want_states=want_states,
+                              lowlevel=False)
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's single-robot signatures
+# ----------------------------------------------------------------------------------------------
+_SOLVERS: Dict[bytes, BatchedMPC] = {}
+
+
+def default_solver(mpc, biped, max_batch: int = 1, extend_gait: bool = False) -> BatchedMPC:
+    """Cached handle for a parameter set (the shim functions are stateless like the reference's)."""
+    key = params_key(pack_params(mpc, biped, extend_gait)) + bytes([max_batch > 1])
+    s = _SOLVERS.get(key)
+    if s is None:
+        s = BatchedMPC(mpc, biped, max_batch=max(1, max_batch), extend_gait=extend_gait)
+        _SOLVERS[key] = s
+    return s
+
+
+def solve_mpc(x_fb, t, foot, mpc, biped, contact):
+    """Drop-in for ``solve_mpc`` (MPC.py:187-304): returns ``(states (h,13), controls (h,12))``.
+
+    Differences from the reference, on purpose: nothing is printed (MPC.py:190-192 prints the
+    references each call); the result is the optimum of the QP the reference builds, to ~1e-7
+    relative, rather than cvxopt's iterate at its default tolerances.
+    """
+    h = int(mpc.h)
+    contact = np.asarray(contact)
+    if contact.shape != (h, 2):
+        raise IndexError(f"contact must have shape ({h}, 2), got {contact.shape} "
+                         "(the reference fails the same way for h != 10 walking, MPC.py:58)")
+    s = default_solver(mpc, biped)
+    out = s.solve_host(np.asarray(x_fb, dtype=np.float64).reshape(1, 12), np.array([float(t)]),
+                       np.asarray(foot, dtype=np.float64).reshape(1, 6), (contact != 0).astype(np.uint8)[None])
+    if int(out["status"][0]) == STATUS_BADINPUT:
+        raise ValueError("solve_mpc: non-finite input or singular euler-rate matrix (pitch = +-pi/2)")
+    return out["states"][0], out["controls"][0]
+
+
+def lowLevelControl(x_fb, t, pf_w, q, qd, mpc, biped, contact, u):
+    """Drop-in for ``lowLevelControl`` (MPC.py:444-470): returns tau (10,1)."""
+    torch = _torch()
+    s = default_solver(mpc, biped)
+    dev, f64 = s.device, torch.float64
+    c0 = (np.asarray(contact)[0, 0:2] != 0).astype(np.uint8).reshape(1, 2)
+    tn = lambda a, shape: torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(shape), dtype=f64, device=dev)
+    tau = s.lowlevel(tn(x_fb, (1, 12)), tn([float(t)], (1,)), tn(pf_w, (1, 6)), tn(q, (1, 10)), tn(qd, (1, 10)),
+                     torch.as_tensor(c0, device=dev), tn(u, (1, 12)))
+    return tau[0].cpu().numpy().reshape(10, 1)
+
+
+def getFootPositionWorld(x_fb, q, biped, mpc=None):
+    """Drop-in for ``getFootPositionWorld`` (MPC.py:406-424): returns pf_w (6,1)."""
+    torch = _torch()
+    s = default_solver(mpc if mpc is not None else MPC(), biped)
+    tn = lambda a, shape: torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(shape), dtype=torch.float64,
+                                          device=s.device)
+    return s.foot_positions(tn(x_fb, (1, 12)), tn(q, (1, 10)))[0].cpu().numpy().reshape(6, 1)

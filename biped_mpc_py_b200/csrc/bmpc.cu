@@ -1,0 +1,355 @@
+// C ABI of the B200-native batched biped MPC (see include/biped_mpc_b200.h).
+// Host side: parameter presolve, workspace, kernel dispatch.  No torch types, no CPU
+// fallback: every entry point either launches the CUDA kernels or returns an error.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+
+#include "../../include/biped_mpc_b200.h"
+#include "bmpc_solve.cuh"
+
+using namespace bmpc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+typedef void (*TickKernel)(const DevParams, const IoPtrs, const int*, const int*);
+
+struct Variant {
+    TickKernel fn = nullptr;
+    size_t smem = 0;
+    int threads = 0;
+    int resident = 0;  // CTAs that fit on the device at once
+};
+
+}  // namespace
+
+struct bmpc_handle {
+    int device = 0;
+    int max_batch = 0;
+    int num_sms = 0;
+    bmpc_params host_params;
+    DevParams dp;
+    Variant bucket[2];
+    int* d_lists = nullptr;   // [2][max_batch]
+    int* d_counts = nullptr;  // [2]
+    int64_t launches = 0;
+};
+
+namespace {
+
+// Host-side presolve of the per-block inequality rows (MPC.py:220-271): which of the six
+// components [fx,fy,fz,mx,my,mz] are free, and which rows are implied by others for these
+// parameter values (dropping them does not change the feasible set).
+int build_dev_params(const bmpc_params& P, DevParams& d) {
+    memset(&d, 0, sizeof(d));
+    if (P.h != 10) return fail("horizon must be 10 in this build (h=30 is not instantiated yet)");
+    d.h = P.h;
+    d.extend = P.extend_gait;
+    d.dt = P.dt;
+    d.kv = P.kv;
+    d.swing_height = P.swing_height;
+    d.mass = P.mass;
+    d.lt_eff = P.lt - 0.01;  // MPC.py:254
+    d.lh_eff = P.lh - 0.02;  // MPC.py:255
+    d.g = P.g;
+    d.mu = P.mu;
+    d.max_iter = P.max_iter > 0 ? P.max_iter : 40;
+    d.mu_tol = P.mu_tol > 0 ? P.mu_tol : 1e-12;
+    d.rd_tol = P.rd_tol > 0 ? P.rd_tol : 1e-9;
+    d.init_fz_frac = 0.1;
+    memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));
+    memcpy(d.Q, P.Q, sizeof(d.Q));
+    memcpy(d.R, P.R, sizeof(d.R));
+    memcpy(d.kp, P.kp, sizeof(d.kp));
+    memcpy(d.kd, P.kd, sizeof(d.kd));
+    memcpy(d.inertia, P.inertia, sizeof(d.inertia));
+    memcpy(d.hip, P.hip_offset, sizeof(d.hip));
+    for (int c = 0; c < 3; ++c) {
+        d.lo6[c] = P.f_min[c];
+        d.hi6[c] = P.f_max[c];
+        d.lo6[3 + c] = P.tau_min[c];
+        d.hi6[3 + c] = P.tau_max[c];
+    }
+    if (!(P.dt > 0) || !(P.mass > 0) || !(P.mu >= 0)) return fail("dt, mass must be positive and mu non-negative");
+    for (int c = 0; c < 6; ++c) {
+        if (!(d.hi6[c] >= d.lo6[c])) return fail("empty box: a *_max is below its *_min");
+        if (d.hi6[c] > d.lo6[c])
+            d.comps[d.LB++] = c;
+        else
+            d.pinned[d.npinned++] = c;
+    }
+    if (d.LB != 5 && d.LB != 6)
+        return fail("unsupported limits: at most one of the six force/moment components may be pinned (min == max)");
+    bool f_free = true;
+    for (int c = 0; c < 3; ++c) f_free = f_free && (d.hi6[c] > d.lo6[c]);
+    auto local = [&](int comp) {
+        for (int c = 0; c < d.LB; ++c)
+            if (d.comps[c] == comp) return c;
+        return -1;
+    };
+    int mb = 0;
+    auto add = [&](int kind, int arg) {
+        d.row_kind[mb] = kind;
+        d.row_arg[mb] = arg;
+        ++mb;
+    };
+    const bool pyramid = f_free && P.mu > 0;
+    for (int c = 0; c < 6; ++c) {  // lower bounds
+        if (local(c) < 0) continue;
+        bool keep = true;
+        if (pyramid && c == 2 && d.lo6[2] <= 0) keep = false;                       // |fx| <= mu fz => fz >= 0
+        if (pyramid && c < 2 && d.lo6[c] <= -P.mu * d.hi6[2]) keep = false;          // fx >= -mu fz >= -mu fz_max
+        if (keep) add(ROW_LO, local(c));
+    }
+    for (int c = 0; c < 6; ++c) {  // upper bounds
+        if (local(c) < 0) continue;
+        bool keep = true;
+        if (pyramid && c < 2 && d.hi6[c] >= P.mu * d.hi6[2]) keep = false;           // fx <= mu fz <= mu fz_max
+        if (keep) add(ROW_HI, local(c));
+    }
+    for (int r = 0; r < 4; ++r) {  // friction pyramid, MPC.py:220-229
+        bool keep = true;
+        // -fx - mu fz <= 0 is implied by fx >= 0 and fz >= 0 (reference defaults: f_min = 0)
+        if (r >= 2 && d.lo6[r - 2] >= 0 && d.lo6[2] >= 0) keep = false;
+        if (keep) add(ROW_FRIC, r);
+    }
+    add(ROW_LINE, 0);  // MPC.py:258-263
+    add(ROW_LINE, 1);
+    d.mb = mb;
+    return 0;
+}
+
+template <int HZ, int SMAX, int LB, int NT>
+int setup_variant(Variant& v, int num_sms) {
+    using L = Layout<HZ, SMAX, LB>;
+    v.fn = mpc_tick_kernel<HZ, SMAX, LB, NT>;
+    v.smem = L::bytes;
+    v.threads = NT;
+    CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, NT, v.smem));
+    if (per_sm < 1) return fail("kernel does not fit on an SM");
+    v.resident = per_sm * num_sms;
+    return 0;
+}
+
+int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n > h->max_batch) return fail("batch larger than max_batch given to bmpc_create");
+    auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
+                 (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
+    classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->d_lists, h->d_counts);
+    for (int b = 0; b < 2; ++b) {
+        const Variant& v = h->bucket[b];
+        // persistent CTAs: as many as fit on the device, each strides over its bucket's work list
+        const int grid = std::min(n, v.resident);
+        v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b);
+    }
+    h->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bmpc_last_error(void) { return g_err.c_str(); }
+int bmpc_abi_version(void) { return BMPC_ABI_VERSION; }
+
+int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handle** out) {
+    if (!params || !out || max_batch <= 0) return fail("bmpc_create: bad arguments");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("bmpc_create: device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("this build targets sm_100a (Blackwell B200) only");
+    bmpc_handle* h = new bmpc_handle();
+    h->device = device;
+    h->max_batch = max_batch;
+    h->num_sms = prop.multiProcessorCount;
+    h->host_params = *params;
+    if (build_dev_params(*params, h->dp)) {
+        delete h;
+        return 1;
+    }
+    int rc = 0;
+    if (h->dp.LB == 5) {
+        rc = setup_variant<10, 10, 5, 128>(h->bucket[0], h->num_sms) ||
+             setup_variant<10, 20, 5, 256>(h->bucket[1], h->num_sms);
+    } else {
+        rc = setup_variant<10, 10, 6, 128>(h->bucket[0], h->num_sms) ||
+             setup_variant<10, 20, 6, 256>(h->bucket[1], h->num_sms);
+    }
+    if (rc) {
+        delete h;
+        return 1;
+    }
+    e = cudaMalloc(&h->d_lists, sizeof(int) * 2 * (size_t)max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 2);
+    if (e != cudaSuccess) {
+        cudaFree(h->d_lists);
+        delete h;
+        return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return 0;
+}
+
+int bmpc_destroy(bmpc_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_lists);
+    cudaFree(h->d_counts);
+    delete h;
+    return 0;
+}
+
+int bmpc_step(bmpc_handle* h, int n, const double* x_fb, const int32_t* phase_k, const double* t_swing,
+              const double* foot, const uint8_t* contact, const double* q, const double* qd, const double* pf_w,
+              double* controls, double* states, double* tau, int32_t* status, int32_t* iters, uint8_t* fric_active,
+              double* resid, void* stream) {
+    if (!h) return fail("bmpc_step: null handle");
+    if (!x_fb || !phase_k || !t_swing || !foot || !contact || !q || !qd || !pf_w || !controls || !tau || !status ||
+        !iters)
+        return fail("bmpc_step: null required pointer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    IoPtrs io;
+    memset(&io, 0, sizeof(io));
+    io.x_fb = x_fb, io.phase_k = phase_k, io.t_swing = t_swing, io.foot = foot, io.contact = contact;
+    io.q = q, io.qd = qd, io.pf_w = pf_w;
+    io.controls = controls, io.states = states, io.tau = tau, io.status = status, io.iters = iters;
+    io.fric_active = fric_active, io.resid = resid;
+    io.do_lowlevel = 1;
+    return launch_tick(h, n, io, static_cast<cudaStream_t>(stream));
+}
+
+int bmpc_solve(bmpc_handle* h, int n, const double* x_fb, const int32_t* phase_k, const double* foot,
+               const uint8_t* contact, double* controls, double* states, int32_t* status, int32_t* iters,
+               uint8_t* fric_active, double* resid, void* stream) {
+    if (!h) return fail("bmpc_solve: null handle");
+    if (!x_fb || !phase_k || !foot || !contact || !controls || !status || !iters)
+        return fail("bmpc_solve: null required pointer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    IoPtrs io;
+    memset(&io, 0, sizeof(io));
+    io.x_fb = x_fb, io.phase_k = phase_k, io.foot = foot, io.contact = contact;
+    io.controls = controls, io.states = states, io.status = status, io.iters = iters;
+    io.fric_active = fric_active, io.resid = resid;
+    io.do_lowlevel = 0;
+    return launch_tick(h, n, io, static_cast<cudaStream_t>(stream));
+}
+
+int bmpc_lowlevel(bmpc_handle* h, int n, const double* x_fb, const double* t_swing, const double* pf_w,
+                  const double* q, const double* qd, const uint8_t* contact0, const double* u0, double* tau,
+                  void* stream) {
+    if (!h) return fail("bmpc_lowlevel: null handle");
+    if (!x_fb || !t_swing || !pf_w || !q || !qd || !contact0 || !u0 || !tau)
+        return fail("bmpc_lowlevel: null required pointer");
+    if (n <= 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int threads = 128, total = 2 * n;
+    lowlevel_kernel<<<(total + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->dp, n, x_fb, t_swing, pf_w, q, qd, contact0, u0, tau);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bmpc_foot_positions(bmpc_handle* h, int n, const double* x_fb, const double* q, double* pf_w, void* stream) {
+    if (!h) return fail("bmpc_foot_positions: null handle");
+    if (!x_fb || !q || !pf_w) return fail("bmpc_foot_positions: null required pointer");
+    if (n <= 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int threads = 128, total = 2 * n;
+    foot_positions_kernel<<<(total + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->dp, n, x_fb, q, pf_w);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bmpc_debug_assemble(bmpc_handle* h, const double* x_fb, const int32_t* phase_k, const double* foot,
+                        const uint8_t* contact, double* Hc_out, double* g_out, int32_t* n_out, void* stream) {
+    if (!h) return fail("bmpc_debug_assemble: null handle");
+    if (!x_fb || !phase_k || !foot || !contact || !Hc_out || !g_out || !n_out)
+        return fail("bmpc_debug_assemble: null required pointer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* scratch = nullptr;  // controls + status + iters for the single instance
+    const int hz = h->dp.h;
+    CUDA_TRY(cudaMalloc(&scratch, sizeof(double) * (hz * 12 + 4)));
+    IoPtrs io;
+    memset(&io, 0, sizeof(io));
+    io.x_fb = x_fb, io.phase_k = phase_k, io.foot = foot, io.contact = contact;
+    io.controls = scratch;
+    io.status = reinterpret_cast<int32_t*>(scratch + hz * 12);
+    io.iters = io.status + 1;
+    io.dbg_H = Hc_out, io.dbg_g = g_out, io.dbg_n = n_out;
+    int rc = launch_tick(h, 1, io, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(std::string("debug kernel: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
+
+int bmpc_measure_fma_peak(int device, int fp64, double* tflops_out) {
+    if (!tflops_out) return fail("bmpc_measure_fma_peak: null output");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    void* buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, sizeof(double) * threads * (size_t)blocks));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        if (fp64)
+            fma_peak_kernel<double><<<blocks, threads>>>(static_cast<double*>(buf), iters);
+        else
+            fma_peak_kernel<float><<<blocks, threads>>>(static_cast<float*>(buf), iters);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    CUDA_TRY(cudaGetLastError());
+    *tflops_out = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+/*
+ * biped_mpc_b200 - C ABI of the B200-native batched HECTOR-style force-and-moment MPC.
+ *
+ * Drop-in boundary for the hot path of /root/reference/bipedalLocomotionMPC.py ("MPC.py"):
+ *   solve_mpc(x_fb, t, foot, mpc, biped, contact) -> (states, controls)      MPC.py:187-304
+ *   lowLevelControl(x_fb, t, pf_w, q, qd, mpc, biped, contact, u) -> tau     MPC.py:444-470
+ * The reference has no FFI layer (two plain Python functions called at MPC.py:487 and
+ * MPC.py:494); these entry points are what a ctypes binding for that path binds, batched
+ * over N independent robots.  Plain pointers and sizes only - no torch / C++ types.
+ *
+ * Conventions
+ *   - All real arrays are float64, row-major, contiguous, DEVICE pointers owned by the
+ *     caller (torch tensor.data_ptr()), unless the function name ends in _host.
+ *   - Every call returns 0 on success, non-zero on failure; bmpc_last_error() gives the text.
+ *   - Calls are asynchronous on the given CUDA stream (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream).  One handle per host thread / stream.
+ *   - State x = [euler(3), pos(3), omega(3), vel(3)] (MPC.py:9), input
+ *     u = [f1(3), f2(3), m1(3), m2(3)] (MPC.py:10).
+ */
+#ifndef BIPED_MPC_B200_H
+#define BIPED_MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMPC_ABI_VERSION 1
+
+/* Mirror of `class MPC` (MPC.py:22-32) + `class Biped` (MPC.py:34-48) + solver options. */
+typedef struct bmpc_params {
+    int32_t h;             /* horizon: 10 or 30                                  MPC.py:24 */
+    int32_t extend_gait;   /* 1: periodic foot-reference extension for h != 10 (new
+                              behaviour, the reference raises IndexError there)           */
+    double dt;             /* MPC.py:25 */
+    double x_cmd[12];      /* MPC.py:26 */
+    double Q[13];          /* MPC.py:27 */
+    double R[12];          /* MPC.py:28 */
+    double kv;             /* MPC.py:29 */
+    double kp[9];          /* row-major 3x3, MPC.py:30 */
+    double kd[9];          /* row-major 3x3, MPC.py:31 */
+    double swing_height;   /* MPC.py:32 */
+    double mass;           /* MPC.py:36 */
+    double inertia[9];     /* row-major 3x3, MPC.py:37-39 */
+    double lt, lh;         /* MPC.py:40-41 (the 0.01 / 0.02 margins of MPC.py:254-255 are applied inside) */
+    double g;              /* MPC.py:42 */
+    double hip_offset[3];  /* MPC.py:43 (used by bmpc_foot_positions only) */
+    double mu;             /* MPC.py:44 */
+    double f_max[3], f_min[3], tau_max[3], tau_min[3]; /* MPC.py:45-48 */
+    /* interior-point options (0 selects the default in brackets) */
+    int32_t max_iter;      /* [40] */
+    int32_t polish;        /* reserved */
+    double mu_tol;         /* [1e-12] complementarity target, objective = reference / 2 */
+    double rd_tol;         /* [1e-9]  stationarity residual (inf-norm)                    */
+} bmpc_params;
+
+typedef struct bmpc_handle bmpc_handle;
+
+/* status[] values written per instance */
+#define BMPC_STATUS_OPTIMAL   0   /* converged to mu_tol / rd_tol                        */
+#define BMPC_STATUS_MAXITER   1   /* iteration cap hit; best iterate returned            */
+#define BMPC_STATUS_NUMERIC   2   /* factorisation broke down near the optimum; iterate returned */
+#define BMPC_STATUS_BADINPUT  3   /* NaN/Inf in inputs or pitch = +-pi/2 (MPC.py:160-164 singular) */
+
+/* Create a solver bound to `device` for batches up to `max_batch`.  Replaces the
+ * construction of `mpc = MPC(); biped = Biped()` (MPC.py:475-476). */
+int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handle** out);
+int bmpc_destroy(bmpc_handle* h);
+
+/* One MPC tick for N robots = solve_mpc (MPC.py:487) + lowLevelControl on controls[0]
+ * (MPC.py:493-494), fused.
+ *   in : x_fb[N,12]  phase_k[N] (int32: int(t // dt) % h computed on the host with the
+ *        reference's float expression, MPC.py:56,99)  t_swing[N] (the t of MPC.py:436)
+ *        foot[N,6] (MPC.py:479)  contact[N,h,2] uint8 (MPC.py:482-484)  q[N,10]  qd[N,10]
+ *        pf_w[N,6]
+ *   out: controls[N,h,12]  states[N,h,13] (nullable)  tau[N,10]  status[N]  iters[N]
+ *        fric_active[N,h] (nullable; bit 4*leg+r = friction row r of MPC.py:220-229 active)
+ *        resid[N,2] (nullable; final complementarity mu and stationarity residual) */
+int bmpc_step(bmpc_handle* h, int n,
+              const double* x_fb, const int32_t* phase_k, const double* t_swing,
+              const double* foot, const uint8_t* contact,
+              const double* q, const double* qd, const double* pf_w,
+              double* controls, double* states, double* tau,
+              int32_t* status, int32_t* iters, uint8_t* fric_active, double* resid,
+              void* stream);
+
+/* solve_mpc only (MPC.py:187-304). */
+int bmpc_solve(bmpc_handle* h, int n,
+               const double* x_fb, const int32_t* phase_k, const double* foot, const uint8_t* contact,
+               double* controls, double* states,
+               int32_t* status, int32_t* iters, uint8_t* fric_active, double* resid,
+               void* stream);
+
+/* lowLevelControl only (MPC.py:444-470): u0[N,12] -> tau[N,10].  contact0[N,2] = contact[0,:]. */
+int bmpc_lowlevel(bmpc_handle* h, int n,
+                  const double* x_fb, const double* t_swing, const double* pf_w,
+                  const double* q, const double* qd, const uint8_t* contact0, const double* u0,
+                  double* tau, void* stream);
+
+/* getFootPositionWorld (MPC.py:406-424) for N robots: x_fb[N,12], q[N,10] -> pf_w[N,6]. */
+int bmpc_foot_positions(bmpc_handle* h, int n, const double* x_fb, const double* q, double* pf_w, void* stream);
+
+/* Debug / parity: the contact-reduced condensed QP of instance `index` of the last
+ * bmpc_step/bmpc_solve inputs.  Hc_out[nmax*nmax] row-major (nmax = 12*h), g_out[nmax],
+ * n_out = number of reduced variables, all DEVICE pointers.  Synchronous. */
+int bmpc_debug_assemble(bmpc_handle* h,
+                        const double* x_fb, const int32_t* phase_k, const double* foot, const uint8_t* contact,
+                        double* Hc_out, double* g_out, int32_t* n_out, void* stream);
+
+/* Number of kernels this handle has launched so far (for bench.py's gpu_launches). */
+int64_t bmpc_launch_count(const bmpc_handle* h);
+
+/* Measured CUDA-core FMA peak of the device (roofline denominator): fp64 != 0 selects
+ * double precision.  Runs a register-resident FMA chain on every SM; result in TFLOP/s. */
+int bmpc_measure_fma_peak(int device, int fp64, double* tflops_out);
+
+const char* bmpc_last_error(void);
+int bmpc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIPED_MPC_B200_H */
