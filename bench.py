@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py - MPC QP solves/sec (horizon 10) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm (reference-class stand-in)
+
+A "step" is one pass of the fused MPC tick (assembly + interior-point solve + torque map) over
+one batch of synthetic randomised biped states; every rank owns an independent
+shard (weak scaling, no data-path collective - SURVEY.md 8e); NCCL is used only for the timing
+max and the final stats reduction.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import os
+
+for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")  # the CPU legs run one process per core
+
+import argparse
+import json
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mpc_qp_solves_per_sec_h10"
+UNIT = "solves/s"
+PER_GPU_BATCH = 262144  # BASELINE.json configs[2]: 262,144 instances per GPU (weak scaling)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="instances per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(batch, n_gpus):
+    return {"workload": f"{batch} independent horizon-10 biped MPC ticks per GPU per step (BASELINE.json configs[2], "
+                        f"weak scaling; 85% walking / 15% standing, SURVEY.md 8d distribution)",
+            "instances_per_gpu": batch, "horizon": 10, "parallelism": f"shard{n_gpus} (independent instances, no hot-path collective)",
+            "l2_policy": "per-step inputs+outputs (~0.37 GB per GPU at 262144) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic FLOPs (DESIGN.md "FLOP model"): 2 per FMA, mathematically required work only
+# ------------------------------------------------------------------------------------------
+def flops_per_solve(S, iters, LB=5, mb=11, h=10, stages=None):
+    n, m = LB * S, mb * S
+    if stages is None:  # walking: one block per stage; standing: two per stage
+        per_stage = max(1, round(S / h))
+        stages = np.repeat(np.arange(h), per_stage)[:S]
+    f_setup = 250.0 * h
+    for jr in range(S):
+        for jc in range(jr + 1):
+            sr = stages[jr]
+            f_setup += (h - 1 - sr) * (2 * 2 * 9 * LB + 2 * 3 * LB * LB) + 2 * 3 * LB * LB
+    f_setup += S * h * 40.0
+    f_iter = n ** 3 / 3.0 + 6.0 * n * n + m * (8.0 * LB + 20.0) + S * mb * LB * (LB + 1.0)
+    return f_setup + iters * f_iter + 600.0
+
+
+def batch_flops(contact, iters):
+    S = contact.reshape(contact.shape[0], -1).sum(axis=1).astype(int)
+    total = {0: 0.0, 1: 0.0}
+    for s_val in np.unique(S):
+        sel = S == s_val
+        cls = 0 if s_val <= 10 else 1
+        it_sum = float(iters[sel].sum())
+        base = flops_per_solve(int(s_val), 0.0)
+        per_it = flops_per_solve(int(s_val), 1.0) - base
+        total[cls] += sel.sum() * base + it_sum * per_it
+    return total
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampled during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM)))
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs
+# ------------------------------------------------------------------------------------------
+def cpu_leg(per_core):
+    from oracle import cpu_baseline
+    r = cpu_baseline.run(per_core=per_core)
+    return {"value": r["solves_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"{r['solves']} synthetic ticks ({per_core} per core, one process per core, 1 BLAS thread each): "
+                      f"reference dense assembly + dense full-size interior point at cvxopt default tolerances "
+                      f"(cvxopt-class stand-in; the real cvxopt is not installable) + lowLevelControl; "
+                      f"{r['ms_per_solve']:.1f} ms per solve per core, of which assembly {r['ms_assembly']:.1f} ms",
+            "per_core_value": r["per_core_solves_per_s"]}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_leg(per_core=8)
+        if i >= args.warmup:
+            vals.append(r)
+    value = float(np.mean([v["value"] for v in vals]))
+    cores = vals[-1]["cores"]
+    n_per_step = 8 * cores
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_per_step / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.batch, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": vals[-1]["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
+    from tools.measure_peaks import measure
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    mpc, biped = MPC(), Biped()
+    n = args.batch
+    batch = synth.make_batch(n, shard_index=rank, mpc=mpc, biped=biped)
+    solver = BatchedMPC(mpc, biped, max_batch=n, device=local_rank)
+    tn = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    d = dict(x_fb=tn(batch["x_fb"]), phase_k=tn(batch["phase_k"], torch.int32), t=tn(batch["t"]), foot=tn(batch["foot"]),
+             contact=tn(batch["contact"], torch.uint8), q=tn(batch["q"]), qd=tn(batch["qd"]), pf_w=tn(batch["pf_w"]))
+
+    def step():
+        return solver.step(d["x_fb"], d["phase_k"], d["t"], d["foot"], d["contact"], d["q"], d["qd"], d["pf_w"])
+
+    # ---- value: inputs resident in HBM, CUDA events on the launching stream --------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = solver.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    launches = solver.launch_count - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    ms_per_step = ms_total / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    iters = out["iters"].cpu().numpy()
+    status = out["status"].cpu().numpy()
+    resid = out["resid"].cpu().numpy()
+
+    # ---- roofline of the two solve kernels (events inside the C ABI, same stream) ---------
+    solver.enable_timing(True)
+    kt = []
+    for _ in range(max(3, min(args.steps, 10))):
+        step()
+        kt.append(solver.last_timing_ms())
+    solver.enable_timing(False)
+    kt = np.array(kt).mean(axis=0)  # classify, walking-class, standing-class
+    fl = batch_flops(batch["contact"], iters)
+    peaks = measure(local_rank)
+    kernels = []
+    for cls, name in ((0, "mpc_tick_kernel<10,10,5,128> (<=10 stance foot-stages: walking)"),
+                      (1, "mpc_tick_kernel<10,20,5,256> (11..20 stance foot-stages: standing)")):
+        ach = fl[cls] / (kt[1 + cls] * 1e-3) / 1e12 if kt[1 + cls] > 0 else 0.0
+        kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
+                        "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"]})
+    dom = int(np.argmax(kt[1:]))
+    roofline = {"bound": "fp64_fma", "achieved": kernels[dom]["achieved_tflops"], "peak": peaks["fp64_fma_tflops"],
+                "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": None,
+                "peak_source": "measured in this run by bmpc_measure_fma_peak (register-resident DFMA chains on all SMs); "
+                               "MEASURED_PEAKS.json carries no FP64 CUDA-core figure",
+                "fp32_fma_peak_tflops": peaks["fp32_fma_tflops"], "dominant_kernel": kernels[dom]["kernel"],
+                "kernels": kernels, "classify_ms": float(kt[0]),
+                "share_of_step": {"walking": float(kt[1] / kt.sum()), "standing": float(kt[2] / kt.sum())}}
+
+    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------
+    tick = solver.pinned_tick(n, lowlevel=True, want_states=False)
+    for k in ("x_fb", "foot", "q", "qd", "pf_w", "t", "phase_k", "contact"):
+        tick.inputs[k][...] = batch[k]
+    for _ in range(args.warmup):
+        tick.run()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = tick.run()
+        _ = float(res["tau"][0, 0])  # host read of the step's result
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tick.h2d_bytes),
+           "d2h_bytes_per_step": int(tick.d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": "BatchedMPC.pinned_tick(n).run(): pinned host -> device, bmpc_step, device -> pinned host, sync"}
+
+    # ---- stats reduction (the only collective): NCCL sum / max over ranks --------------------
+    stats_sum = torch.tensor([float(n), float(iters.sum()), float((status != 0).sum()), float((status == 3).sum())],
+                             dtype=torch.float64, device=dev)
+    stats_max = torch.tensor([float(iters.max()), float(resid[:, 0].max()), float(resid[:, 1].max())],
+                             dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats_sum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(stats_max, op=dist.ReduceOp.MAX)
+    ssum, smax = stats_sum.cpu().numpy(), stats_max.cpu().numpy()
+
+    line = None
+    if rank == 0:
+        # single-instance latency through the reference-signature path (N=1, launch + copies + sync)
+        latency = None
+        if not args.no_latency:
+            one = BatchedMPC(mpc, biped, max_batch=1, device=local_rank)
+            t1 = one.pinned_tick(1)
+            for k in ("x_fb", "foot", "q", "qd", "pf_w", "t", "phase_k", "contact"):
+                t1.inputs[k][...] = batch[k][:1]
+            lat = []
+            for i in range(230):
+                a = time.perf_counter()
+                t1.run()
+                lat.append(time.perf_counter() - a)
+            lat = np.array(lat[30:]) * 1e3
+            latency = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "samples": len(lat),
+                       "what": "N=1 tick, pinned host in -> tau/controls on host, includes launch + copies + sync"}
+            one.close()
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_leg(per_core=12)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
+                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu, "latency": latency,
+                "solver": {"mean_iters": float(ssum[1] / ssum[0]), "max_iters": int(smax[0]),
+                           "not_optimal": int(ssum[2]), "bad_input": int(ssum[3]), "max_mu": float(smax[1]),
+                           "max_rd": float(smax[2]), "instances": int(ssum[0])}}
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: spawn it ourselves
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

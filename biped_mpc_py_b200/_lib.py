@@ -10,7 +10,7 @@ from .params import BmpcParams
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbiped_mpc_b200.so")
 
 EXPORTS = ["bmpc_create", "bmpc_destroy", "bmpc_step", "bmpc_solve", "bmpc_lowlevel", "bmpc_foot_positions",
-           "bmpc_debug_assemble", "bmpc_launch_count", "bmpc_measure_fma_peak", "bmpc_last_error",
+           "bmpc_debug_assemble", "bmpc_launch_count", "bmpc_enable_timing", "bmpc_last_timing", "bmpc_measure_fma_peak", "bmpc_last_error",
            "bmpc_abi_version"]
 
 _lib = None
@@ -48,6 +48,10 @@ def load():
     lib.bmpc_debug_assemble.restype = c_int
     lib.bmpc_launch_count.argtypes = [c_void_p]
     lib.bmpc_launch_count.restype = c_int64
+    lib.bmpc_enable_timing.argtypes = [c_void_p, c_int]
+    lib.bmpc_enable_timing.restype = c_int
+    lib.bmpc_last_timing.argtypes = [c_void_p, POINTER(ctypes.c_float)]
+    lib.bmpc_last_timing.restype = c_int
     lib.bmpc_measure_fma_peak.argtypes = [c_int, c_int, POINTER(c_double)]
     lib.bmpc_measure_fma_peak.restype = c_int
     lib.bmpc_last_error.argtypes = []

@@ -81,6 +81,15 @@ class BatchedMPC:
     def launch_count(self) -> int:
         return int(self._lib.bmpc_launch_count(self._h))
 
+    def enable_timing(self, on: bool = True):
+        _lib.check(self._lib.bmpc_enable_timing(self._h, int(on)))
+
+    def last_timing_ms(self):
+        """(classify, walking-class kernel, standing-class kernel) device times of the last tick."""
+        ms = (ctypes.c_float * 3)()
+        _lib.check(self._lib.bmpc_last_timing(self._h, ms))
+        return [float(v) for v in ms]
+
     # ------------------------------------------------------------------ helpers
     def _check(self, t, shape, dtype, name):
         torch = _torch()
@@ -208,6 +217,10 @@ class BatchedMPC:
             off = _align(off + nbytes)
         return lay, off
 
+    def pinned_tick(self, n: int, lowlevel: bool = True, want_states: bool = False) -> "PinnedTick":
+        """Zero-copy host interface: numpy views into pinned staging to fill, then ``run()``."""
+        return PinnedTick(self, n, lowlevel, want_states)
+
     def step_host(self, x_fb, t, foot, contact, q, qd, pf_w, phase_k=None, want_states: bool = False,
                   lowlevel: bool = True):
         """End-to-end tick with HOST numpy inputs and outputs (one H2D and one D2H copy).
@@ -217,75 +230,86 @@ class BatchedMPC:
         Returns dict of numpy arrays: controls (N,h,12), tau (N,10), status, iters, fric_active, resid
         and optionally states (N,h,13).  Synchronous.
         """
-        torch = _torch()
         x_fb = np.ascontiguousarray(x_fb, dtype=np.float64).reshape(-1, 12)
         n, h = x_fb.shape[0], self.h
-        if n > self.max_batch:
-            raise ValueError("batch larger than max_batch")
         t = np.ascontiguousarray(t, dtype=np.float64).reshape(n)
         if phase_k is None:
             period = 10 if self.extend_gait else h
             phase_k = (gait_phase(t, self.mpc) % period)
-        st = self._staging()
-        ins = [("x_fb", x_fb), ("foot", np.asarray(foot, dtype=np.float64).reshape(n, 6))]
+        tick = self.pinned_tick(n, lowlevel, want_states)
+        ins = tick.inputs
+        ins["x_fb"][...] = x_fb
+        ins["foot"][...] = np.asarray(foot, dtype=np.float64).reshape(n, 6)
+        ins["phase_k"][...] = np.asarray(phase_k, dtype=np.int32).reshape(n)
+        ins["contact"][...] = np.asarray(contact, dtype=np.uint8).reshape(n, h, 2)
         if lowlevel:
-            ins += [("q", np.asarray(q, dtype=np.float64).reshape(n, 10)),
-                    ("qd", np.asarray(qd, dtype=np.float64).reshape(n, 10)),
-                    ("pf_w", np.asarray(pf_w, dtype=np.float64).reshape(n, 6)), ("t", t)]
-        ins += [("phase_k", np.asarray(phase_k, dtype=np.int32).reshape(n)),
-                ("contact", np.asarray(contact, dtype=np.uint8).reshape(n, h, 2))]
-        lay_in, in_used = self._carve([(k, v.nbytes) for k, v in ins])
-        hin = st["h_in_np"]
-        for k, v in ins:
-            off, nb = lay_in[k]
-            hin[off:off + nb] = v.reshape(-1).view(np.uint8)
-        outs = [("controls", n * h * 12 * 8)]
-        if lowlevel:
-            outs.append(("tau", n * 10 * 8))
-        if want_states:
-            outs.append(("states", n * h * 13 * 8))
-        outs += [("resid", n * 2 * 8), ("status", n * 4), ("iters", n * 4), ("fric", n * h)]
-        lay_out, out_used = self._carve(outs)
-        stream = torch.cuda.current_stream(self.device)
-        st["d_in"][:in_used].copy_(st["h_in"][:in_used], non_blocking=True)
-        din, dout = st["d_in"].data_ptr(), st["d_out"].data_ptr()
-        P = lambda base, lay, k: ctypes.c_void_p(base + lay[k][0]) if k in lay else ctypes.c_void_p(0)
-        sp = ctypes.c_void_p(stream.cuda_stream)
-        if lowlevel:
-            _lib.check(self._lib.bmpc_step(
-                self._h, n, P(din, lay_in, "x_fb"), P(din, lay_in, "phase_k"), P(din, lay_in, "t"),
-                P(din, lay_in, "foot"), P(din, lay_in, "contact"), P(din, lay_in, "q"), P(din, lay_in, "qd"),
-                P(din, lay_in, "pf_w"), P(dout, lay_out, "controls"), P(dout, lay_out, "states"),
-                P(dout, lay_out, "tau"), P(dout, lay_out, "status"), P(dout, lay_out, "iters"),
-                P(dout, lay_out, "fric"), P(dout, lay_out, "resid"), sp))
-        else:
-            _lib.check(self._lib.bmpc_solve(
-                self._h, n, P(din, lay_in, "x_fb"), P(din, lay_in, "phase_k"), P(din, lay_in, "foot"),
-                P(din, lay_in, "contact"), P(dout, lay_out, "controls"), P(dout, lay_out, "states"),
-                P(dout, lay_out, "status"), P(dout, lay_out, "iters"), P(dout, lay_out, "fric"),
-                P(dout, lay_out, "resid"), sp))
-        st["h_out"][:out_used].copy_(st["d_out"][:out_used], non_blocking=True)
-        stream.synchronize()
-        ho = st["h_out_np"]
-
-        def take(name, dtype, shape):
-            off, nb = lay_out[name]
-            return ho[off:off + nb].view(dtype).reshape(shape).copy()
-
-        res = dict(controls=take("controls", np.float64, (n, h, 12)), status=take("status", np.int32, (n,)),
-                   iters=take("iters", np.int32, (n,)), fric_active=take("fric", np.uint8, (n, h)),
-                   resid=take("resid", np.float64, (n, 2)))
-        if lowlevel:
-            res["tau"] = take("tau", np.float64, (n, 10))
-        if want_states:
-            res["states"] = take("states", np.float64, (n, h, 13))
-        self.last_h2d_bytes, self.last_d2h_bytes = int(in_used), int(out_used)
-        return res
+            ins["q"][...] = np.asarray(q, dtype=np.float64).reshape(n, 10)
+            ins["qd"][...] = np.asarray(qd, dtype=np.float64).reshape(n, 10)
+            ins["pf_w"][...] = np.asarray(pf_w, dtype=np.float64).reshape(n, 6)
+            ins["t"][...] = t
+        out = tick.run()
+        self.last_h2d_bytes, self.last_d2h_bytes = tick.h2d_bytes, tick.d2h_bytes
+        return {k: v.copy() for k, v in out.items()}
 
     def solve_host(self, x_fb, t, foot, contact, phase_k=None, want_states: bool = True):
         """``solve_mpc`` only, host numpy in / out."""
         return self.step_host(x_fb, t, foot, contact, None, None, None, phase_k=phase_k, want_states=want_states,
                               lowlevel=False)
+
+
+class PinnedTick:
+    """One batch size's packed pinned layout: fill ``inputs`` (numpy views), call ``run()``.
+
+    ``run()`` = one ``cudaMemcpyAsync`` host->device of the packed inputs, the fused kernels, one
+    device->host copy of the packed outputs, a stream synchronise; it returns numpy views into the
+    pinned output buffer (valid until the next ``run()`` of any tick of the same solver).
+    """
+
+    def __init__(self, solver: BatchedMPC, n: int, lowlevel: bool, want_states: bool):
+        if n > solver.max_batch or n <= 0:
+            raise ValueError("batch size out of range")
+        self.s, self.n, self.lowlevel, self.want_states = solver, n, lowlevel, want_states
+        h = solver.h
+        st = solver._staging()
+        ins = [("x_fb", np.float64, (n, 12)), ("foot", np.float64, (n, 6))]
+        if lowlevel:
+            ins += [("q", np.float64, (n, 10)), ("qd", np.float64, (n, 10)), ("pf_w", np.float64, (n, 6)),
+                    ("t", np.float64, (n,))]
+        ins += [("phase_k", np.int32, (n,)), ("contact", np.uint8, (n, h, 2))]
+        outs = [("controls", np.float64, (n, h, 12))]
+        if lowlevel:
+            outs.append(("tau", np.float64, (n, 10)))
+        if want_states:
+            outs.append(("states", np.float64, (n, h, 13)))
+        outs += [("resid", np.float64, (n, 2)), ("status", np.int32, (n,)), ("iters", np.int32, (n,)),
+                 ("fric_active", np.uint8, (n, h))]
+        nbytes = lambda dt, shp: int(np.dtype(dt).itemsize * int(np.prod(shp)))
+        self.lay_in, self.h2d_bytes = BatchedMPC._carve([(k, nbytes(dt, shp)) for k, dt, shp in ins])
+        self.lay_out, self.d2h_bytes = BatchedMPC._carve([(k, nbytes(dt, shp)) for k, dt, shp in outs])
+        view = lambda buf, lay, k, dt, shp: buf[lay[k][0]:lay[k][0] + lay[k][1]].view(dt).reshape(shp)
+        self.inputs = {k: view(st["h_in_np"], self.lay_in, k, dt, shp) for k, dt, shp in ins}
+        self.outputs = {k: view(st["h_out_np"], self.lay_out, k, dt, shp) for k, dt, shp in outs}
+        self._st = st
+
+    def run(self):
+        torch = _torch()
+        s, st, n = self.s, self._st, self.n
+        stream = torch.cuda.current_stream(s.device)
+        st["d_in"][:self.h2d_bytes].copy_(st["h_in"][:self.h2d_bytes], non_blocking=True)
+        din, dout = st["d_in"].data_ptr(), st["d_out"].data_ptr()
+        I = lambda k: ctypes.c_void_p(din + self.lay_in[k][0])
+        O = lambda k: ctypes.c_void_p(dout + self.lay_out[k][0]) if k in self.lay_out else ctypes.c_void_p(0)
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        if self.lowlevel:
+            _lib.check(s._lib.bmpc_step(s._h, n, I("x_fb"), I("phase_k"), I("t"), I("foot"), I("contact"), I("q"),
+                                        I("qd"), I("pf_w"), O("controls"), O("states"), O("tau"), O("status"),
+                                        O("iters"), O("fric_active"), O("resid"), sp))
+        else:
+            _lib.check(s._lib.bmpc_solve(s._h, n, I("x_fb"), I("phase_k"), I("foot"), I("contact"), O("controls"),
+                                         O("states"), O("status"), O("iters"), O("fric_active"), O("resid"), sp))
+        st["h_out"][:self.d2h_bytes].copy_(st["d_out"][:self.d2h_bytes], non_blocking=True)
+        stream.synchronize()
+        return self.outputs
 
 
 # ----------------------------------------------------------------------------------------------

@@ -50,6 +50,8 @@ struct bmpc_handle {
     int* d_lists = nullptr;   // [2][max_batch]
     int* d_counts = nullptr;  // [2]
     int64_t launches = 0;
+    int timing = 0;              // record CUDA events around each kernel of a tick
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -157,12 +159,15 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
                  (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
     CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
-    classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->d_lists, h->d_counts);
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
     for (int b = 0; b < 2; ++b) {
         const Variant& v = h->bucket[b];
         // persistent CTAs: as many as fit on the device, each strides over its bucket's work list
         const int grid = std::min(n, v.resident);
         v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b);
+        if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2 + b], st));
     }
     h->launches += 3;
     CUDA_TRY(cudaGetLastError());
@@ -224,6 +229,8 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_lists);
     cudaFree(h->d_counts);
+    for (int i = 0; i < 4; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return 0;
 }
@@ -318,6 +325,23 @@ int bmpc_debug_assemble(bmpc_handle* h, const double* x_fb, const int32_t* phase
 }
 
 int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
+
+int bmpc_enable_timing(bmpc_handle* h, int enable) {
+    if (!h) return fail("bmpc_enable_timing: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (enable && !h->ev[0])
+        for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    h->timing = enable ? 1 : 0;
+    return 0;
+}
+
+int bmpc_last_timing(bmpc_handle* h, float* ms3) {
+    if (!h || !ms3 || !h->ev[0]) return fail("bmpc_last_timing: timing was not enabled");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->ev[3]));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms3[i], h->ev[i], h->ev[i + 1]));
+    return 0;
+}
 
 int bmpc_measure_fma_peak(int device, int fp64, double* tflops_out) {
     if (!tflops_out) return fail("bmpc_measure_fma_peak: null output");

@@ -41,7 +41,6 @@ __global__ void __launch_bounds__(NT) mpc_tick_kernel(const __grid_constant__ De
     double* wrow = sm + L::o_wrow;
     double* drow = sm + L::o_drow;
     double* red = sm + L::o_red;
-    double* scal = red + 32;
     int* blk_stage = reinterpret_cast<int*>(sm + L::o_int);
     int* blk_foot = blk_stage + SMAX;
     int* blockOf = blk_foot + SMAX;   // [HZ][2]
@@ -585,7 +584,7 @@ __global__ void __launch_bounds__(NT) mpc_tick_kernel(const __grid_constant__ De
                 const double mu_aff = block_sum<NT>(part, red) / (double)m;
                 double sigma = mu_aff / mu;
                 sigma = sigma * sigma * sigma;
-                // corrector: M dcorr = -C' ((dsa*dla - sigma*mu) / s)
+                // corrector: M dcorr = +C' ((dsa*dla - sigma*mu) / s)
                 double wc_[RPT];
 #pragma unroll
                 for (int rr = 0; rr < RPT; ++rr) {
@@ -596,7 +595,7 @@ __global__ void __launch_bounds__(NT) mpc_tick_kernel(const __grid_constant__ De
                     }
                 }
                 __syncthreads();
-                if (tid < n) xv[tid] = -col_gather(tid, wrow);
+                if (tid < n) xv[tid] = col_gather(tid, wrow);
                 __syncthreads();
                 solve_forward<NT>(Mp, n, inv, xv);
                 solve_backward<NT>(Mp, n, inv, xv);
@@ -729,8 +728,8 @@ __global__ void __launch_bounds__(NT) mpc_tick_kernel(const __grid_constant__ De
 // ------------------------------------------------------------------------------------
 
 // bucket instances by number of stance foot-stages: list0 = S <= h, list1 = the rest
-__global__ void classify_kernel(const uint8_t* __restrict__ contact, int n, int h, int* __restrict__ lists,
-                                int* __restrict__ counts) {
+__global__ void classify_kernel(const uint8_t* __restrict__ contact, int n, int h, int list_stride,
+                                int* __restrict__ lists, int* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int S = 0;
@@ -738,7 +737,7 @@ __global__ void classify_kernel(const uint8_t* __restrict__ contact, int n, int 
     const int b = (S <= h) ? 0 : 1;
     // order inside a bucket does not affect any result (instances are independent)
     const int slot = atomicAdd(&counts[b], 1);
-    lists[(size_t)b * n + slot] = i;
+    lists[(size_t)b * list_stride + slot] = i;
 }
 
 // lowLevelControl only (MPC.py:444-470): one thread per (instance, leg)

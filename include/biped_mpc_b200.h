@@ -111,6 +111,12 @@ int bmpc_debug_assemble(bmpc_handle* h,
 /* Number of kernels this handle has launched so far (for bench.py's gpu_launches). */
 int64_t bmpc_launch_count(const bmpc_handle* h);
 
+/* Per-kernel device timing of the last bmpc_step/bmpc_solve (CUDA events on the launching
+ * stream): ms3 = {classify, walking-class kernel (<= h stance foot-stages), standing-class
+ * kernel}.  bmpc_last_timing blocks until the tick has finished. */
+int bmpc_enable_timing(bmpc_handle* h, int enable);
+int bmpc_last_timing(bmpc_handle* h, float* ms3);
+
 /* Measured CUDA-core FMA peak of the device (roofline denominator): fp64 != 0 selects
  * double precision.  Runs a register-resident FMA chain on every SM; result in TFLOP/s. */
 int bmpc_measure_fma_peak(int device, int fp64, double* tflops_out);
