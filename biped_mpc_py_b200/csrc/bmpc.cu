@@ -12,6 +12,7 @@
 
 #include "../../include/biped_mpc_b200.h"
 #include "bmpc_solve.cuh"
+#include "bmpc_tick.cuh"
 
 using namespace bmpc;
 
@@ -29,13 +30,15 @@ int fail(const std::string& msg) {
         if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
-typedef void (*TickKernel)(const DevParams, const IoPtrs, const int*, const int*);
+typedef void (*TickKernel)(const DevParams, const IoPtrs, const int*, const int*, double*);
 
 struct Variant {
     TickKernel fn = nullptr;
     size_t smem = 0;
     int threads = 0;
     int resident = 0;  // CTAs that fit on the device at once
+    size_t scratch_doubles = 0;  // per resident CTA: one copy of the tile matrix H
+    double* d_scratch = nullptr;
 };
 
 }  // namespace
@@ -73,8 +76,9 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     d.g = P.g;
     d.mu = P.mu;
     d.max_iter = P.max_iter > 0 ? P.max_iter : 40;
-    d.mu_tol = P.mu_tol > 0 ? P.mu_tol : 1e-12;
-    d.rd_tol = P.rd_tol > 0 ? P.rd_tol : 1e-9;
+    d.mu_tol = P.mu_tol > 0 ? P.mu_tol : 1e-7;
+    d.rd_tol = P.rd_tol > 0 ? P.rd_tol : 10.0;
+    d.gondzio = 1;
     d.init_fz_frac = 0.1;
     memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));
     memcpy(d.Q, P.Q, sizeof(d.Q));
@@ -139,16 +143,18 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
 }
 
 template <int HZ, int SMAX, int LB, int NT>
-int setup_variant(Variant& v, int num_sms) {
-    using L = Layout<HZ, SMAX, LB>;
-    v.fn = mpc_tick_kernel<HZ, SMAX, LB, NT>;
-    v.smem = L::bytes;
+int setup_variant(Variant& v, int num_sms, int mb) {
+    using L = TickLayout<HZ, SMAX, LB>;
+    v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT>;
+    v.smem = L::bytes(mb);
     v.threads = NT;
+    v.scratch_doubles = L::MB;
     CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, NT, v.smem));
     if (per_sm < 1) return fail("kernel does not fit on an SM");
     v.resident = per_sm * num_sms;
+    CUDA_TRY(cudaMalloc(&v.d_scratch, sizeof(double) * v.scratch_doubles * (size_t)v.resident));
     return 0;
 }
 
@@ -166,7 +172,8 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         const Variant& v = h->bucket[b];
         // persistent CTAs: as many as fit on the device, each strides over its bucket's work list
         const int grid = std::min(n, v.resident);
-        v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b);
+        v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b,
+                                               v.d_scratch);
         if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2 + b], st));
     }
     h->launches += 3;
@@ -203,11 +210,11 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
     }
     int rc = 0;
     if (h->dp.LB == 5) {
-        rc = setup_variant<10, 10, 5, 128>(h->bucket[0], h->num_sms) ||
-             setup_variant<10, 20, 5, 256>(h->bucket[1], h->num_sms);
+        rc = setup_variant<10, 10, 5, 32>(h->bucket[0], h->num_sms, h->dp.mb) ||
+             setup_variant<10, 20, 5, 128>(h->bucket[1], h->num_sms, h->dp.mb);
     } else {
-        rc = setup_variant<10, 10, 6, 128>(h->bucket[0], h->num_sms) ||
-             setup_variant<10, 20, 6, 256>(h->bucket[1], h->num_sms);
+        rc = setup_variant<10, 10, 6, 32>(h->bucket[0], h->num_sms, h->dp.mb) ||
+             setup_variant<10, 20, 6, 128>(h->bucket[1], h->num_sms, h->dp.mb);
     }
     if (rc) {
         delete h;
@@ -229,6 +236,7 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_lists);
     cudaFree(h->d_counts);
+    for (int b = 0; b < 2; ++b) cudaFree(h->bucket[b].d_scratch);
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;

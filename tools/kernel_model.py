@@ -260,7 +260,7 @@ def sweep_inverse(M):
     return -A
 
 
-def ipm_model(red, tol=1e-11, maxit=40, prune=True, init_fz_frac=0.1, refine=0, use_sweep=True, verbose=False, chol=False, rd_fac=10.0, abs_tol=None):
+def ipm_model(red, tol=1e-11, maxit=40, prune=True, init_fz_frac=0.1, refine=0, use_sweep=True, verbose=False, chol=False, rd_fac=10.0, abs_tol=None, return_state=False):
     Cb, rb, tags = block_rows(red, prune)
     nb, LB = len(red["blocks"]), red["LB"]
     n, mb = nb * LB, len(rb)
@@ -342,4 +342,178 @@ def ipm_model(red, tol=1e-11, maxit=40, prune=True, init_fz_frac=0.1, refine=0, 
         du, ds, dl = newton(s * lam + ds * dl - sigma * mu)
         a = min(1.0, 0.995 * min(max_step(s, ds), max_step(lam, dl)))
         u, s, lam = u + a * du, s + a * ds, lam + a * dl
+    if return_state:
+        return u, it, hist, s, lam
     return u, it, hist
+
+
+# ----------------------------------------------------------------------------
+# model of the kernel's active-set polish (written the way the CUDA code does it)
+# ----------------------------------------------------------------------------
+
+def block_nullspace(A, b, tol=1e-10):
+    """Affine set {x : A x = b} of one block by Gauss-Jordan with complete pivoting.
+
+    Returns (p, N, ok): particular solution p (free variables 0), basis N (LB x d) of the null
+    space, ok=False if the rows are inconsistent.  A is k x LB with k possibly > LB or rank deficient.
+    """
+    A = np.array(A, dtype=float, copy=True)
+    b = np.array(b, dtype=float, copy=True)
+    k, LB = A.shape
+    scale = max(1.0, np.abs(A).max()) if k else 1.0
+    piv_col = []
+    piv_row = []
+    used_r = np.zeros(k, bool)
+    used_c = np.zeros(LB, bool)
+    for _ in range(min(k, LB)):
+        best, br, bc = 0.0, -1, -1
+        for r in range(k):
+            if used_r[r]:
+                continue
+            for c in range(LB):
+                if not used_c[c] and abs(A[r, c]) > best:
+                    best, br, bc = abs(A[r, c]), r, c
+        if best <= tol * scale:
+            break
+        used_r[br] = used_c[bc] = True
+        piv_row.append(br)
+        piv_col.append(bc)
+        inv = 1.0 / A[br, bc]
+        A[br] *= inv
+        b[br] *= inv
+        for r in range(k):
+            if r != br and A[r, bc] != 0.0:
+                f = A[r, bc]
+                A[r] -= f * A[br]
+                b[r] -= f * b[br]
+    ok = True
+    for r in range(k):
+        if not used_r[r] and abs(b[r]) > 1e-7 * max(1.0, np.abs(b).max()):
+            ok = False
+    free = [c for c in range(LB) if not used_c[c]]
+    p = np.zeros(LB)
+    N = np.zeros((LB, len(free)))
+    for r, c in zip(piv_row, piv_col):
+        p[c] = b[r]
+    for jf, c in enumerate(free):
+        N[c, jf] = 1.0
+        for r, pc in zip(piv_row, piv_col):
+            N[pc, jf] = -A[r, c]
+    return p, N, ok
+
+
+def tiny_nnls(A, r, tol=1e-12, maxit=40):
+    """Lawson-Hanson: min |A' y - r|, y >= 0, for A (k x LB) with k <= ~18.  Returns y, residual vector."""
+    k, LB = A.shape
+    y = np.zeros(k)
+    passive = np.zeros(k, bool)
+    res = r.copy()
+    w = A @ res
+    scale = max(1.0, np.abs(r).max())
+    for _ in range(maxit):
+        cand = np.where(~passive, w, -np.inf)
+        j = int(np.argmax(cand)) if k else -1
+        if k == 0 or cand[j] <= tol * scale * max(1.0, np.abs(A[j]).max()):
+            break
+        passive[j] = True
+        for _inner in range(maxit):
+            idx = np.nonzero(passive)[0]
+            Ap = A[idx]
+            G = Ap @ Ap.T
+            G[np.diag_indices_from(G)] += 1e-30
+            try:
+                z = np.linalg.solve(G, Ap @ r)
+            except np.linalg.LinAlgError:
+                z = np.linalg.lstsq(Ap.T, r, rcond=None)[0]
+            if (z > 0).all():
+                y[:] = 0.0
+                y[idx] = z
+                break
+            neg = z <= 0
+            alpha = np.min(y[idx][neg] / (y[idx][neg] - z[neg]))
+            y[idx] = y[idx] + alpha * (z - y[idx])
+            drop = idx[(y[idx] <= 1e-300) | ((z <= 0) & (np.abs(y[idx]) <= 1e-14 * max(1.0, np.abs(y).max())))]
+            passive[drop] = False
+            y[drop] = 0.0
+            if not passive.any():
+                break
+        res = r - A.T @ y
+        w = A @ res
+    return y, res
+
+
+def polish_model(red, u, s, lam, max_rounds=4, verbose=False):
+    """Active-set polish from an interior-point iterate.  Returns (u_polished, ok, rounds)."""
+    Cb, rb, tags = block_rows(red, True)
+    nb, LB = len(red["blocks"]), red["LB"]
+    mb = len(rb)
+    n = nb * LB
+    H, g = red["Hc"], red["g"]
+    gs = 1.0 + np.abs(g).max()
+    d = lam / s
+    hdiag = np.diag(H)
+    active = np.zeros((nb, mb), bool)
+    for j in range(nb):
+        for k in range(mb):
+            a = Cb[k]
+            eta = (a * a) @ hdiag[LB * j:LB * j + LB] / max((a @ a) ** 2, 1e-300)
+            active[j, k] = d[j * mb + k] > eta
+    for rnd in range(1, max_rounds + 1):
+        P = np.zeros(n)
+        Ns = []
+        ok = True
+        for j in range(nb):
+            rows = np.nonzero(active[j])[0]
+            p, N, okj = block_nullspace(Cb[rows], rb[rows])
+            ok = ok and okj
+            P[LB * j:LB * j + LB] = p
+            Ns.append(N)
+        if not ok:
+            return u, False, rnd
+        dims = [N.shape[1] for N in Ns]
+        nw = sum(dims)
+        Nfull = np.zeros((n, nw))
+        o = 0
+        for j, N in enumerate(Ns):
+            Nfull[LB * j:LB * j + LB, o:o + dims[j]] = N
+            o += dims[j]
+        if nw:
+            Hr = Nfull.T @ H @ Nfull
+            gr = Nfull.T @ (H @ P + g)
+            try:
+                w = np.linalg.solve(Hr, -gr)
+            except np.linalg.LinAlgError:
+                return u, False, rnd
+            up = P + Nfull @ w
+        else:
+            up = P
+        changed = False
+        # primal check
+        for j in range(nb):
+            viol = Cb @ up[LB * j:LB * j + LB] - rb
+            add = (viol > 1e-9 * (1.0 + np.abs(rb))) & ~active[j]
+            if add.any():
+                active[j] |= add
+                changed = True
+        if changed:
+            if verbose:
+                print("round", rnd, "added violated rows")
+            continue
+        # dual check
+        grad = H @ up + g
+        for j in range(nb):
+            rows = np.nonzero(active[j])[0]
+            rj = -grad[LB * j:LB * j + LB]
+            y, res = tiny_nnls(Cb[rows], rj)
+            if np.abs(res).max() > 1e-9 * gs:
+                wv = Cb[rows] @ res
+                drop = rows[(wv < -1e-12 * gs) & (y <= 0)]
+                if len(drop) == 0:
+                    return u, False, rnd
+                active[j, drop] = False
+                changed = True
+        if not changed:
+            return up, True, rnd
+        if verbose:
+            print("round", rnd, "dropped rows")
+    return u, False, max_rounds
