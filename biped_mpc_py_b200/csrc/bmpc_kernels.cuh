@@ -311,7 +311,7 @@ __device__ __forceinline__ void leg_jacobian(const double* q, double side, doubl
 }
 
 // tau_leg[5] for one leg.  R = eul2rotm(x_fb[0:3]); u = [f1,f2,m1,m2] first-stage input.
-__device__ inline void lowlevel_leg(const DevParams& p, const double* x_fb, double t, const double* pf_w,
+__device__ __noinline__ void lowlevel_leg(const DevParams& p, const double* x_fb, double t, const double* pf_w,
                                     const double* q, const double* qd, const double* R, int leg, double c_leg,
                                     const double* u, double* tau_leg) {
     const double side = (leg == 0) ? 1.0 : -1.0;

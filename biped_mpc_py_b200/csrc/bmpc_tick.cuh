@@ -53,6 +53,25 @@ __device__ __forceinline__ double gmax(double v, double* red) {
     return t;
 }
 template <int NT>
+__device__ __forceinline__ float gmaxf(float v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if constexpr (NT == 32) return v;
+    float* redf = reinterpret_cast<float*>(red);
+    if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = redf[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) t = fmaxf(t, redf[w]);
+    __syncthreads();
+    return t;
+}
+// -dv / v as a float, for the step-length ratio test (a relative error of 1e-7 in a step length that is
+// cut by 0.995 afterwards is harmless).  NaN/Inf propagate so a broken direction is still detected.
+__device__ __forceinline__ float step_ratio(double dv, double v) {
+    return __fdividef(-(float)dv, (float)v);
+}
+template <int NT>
 __device__ __forceinline__ int gany(int pred) {
     if constexpr (NT == 32) return __any_sync(0xffffffffu, pred);
     else return __syncthreads_or(pred);
@@ -136,7 +155,7 @@ __device__ __forceinline__ bool tile_chol_inv(const double (&a)[LB * LB], double
 // jr > jc, holds L(jr,jc) and the diagonal tile (j,j) holds inv(L(j,j)) (the solves only ever
 // need the inverse).  Uniform return value.
 template <int LB, int NT>
-__device__ bool tile_factor(double* __restrict__ Mb, int S) {
+__device__ __noinline__ bool tile_factor(double* __restrict__ Mb, int S) {
     constexpr int E = LB * LB, TS = TileT<LB>::TS;
     const int tid = threadIdx.x;
     bool ok = true;
@@ -196,7 +215,7 @@ __device__ bool tile_factor(double* __restrict__ Mb, int S) {
 
 // x <- inv(L L') x with the factor of tile_factor.  x has LB*S entries in shared memory.
 template <int LB, int NT>
-__device__ void tile_solve(const double* __restrict__ Mb, int S, double* __restrict__ x) {
+__device__ __noinline__ void tile_solve(const double* __restrict__ Mb, int S, double* __restrict__ x) {
     constexpr int TS = TileT<LB>::TS;
     const int tid = threadIdx.x;
     // forward: y_j = Li_j (x_j - sum_{p<j} L(j,p) y_p), column oriented
@@ -253,19 +272,21 @@ __device__ void tile_solve(const double* __restrict__ Mb, int S, double* __restr
 
 // out = H v (+ add) from the symmetric tile matrix (diagonal tiles stored in full)
 template <int LB, int NT>
-__device__ void tile_symv(const double* __restrict__ Mb, int S, const double* __restrict__ v,
+__device__ __noinline__ void tile_symv(const double* __restrict__ Mb, int S, const double* __restrict__ v,
                           const double* __restrict__ add, double* __restrict__ out) {
     constexpr int TS = TileT<LB>::TS;
     const int n = S * LB;
     for (int i = threadIdx.x; i < n; i += NT) {
         const int j = i / LB, a = i - j * LB;
         double acc = add ? add[i] : 0.0;
+#pragma unroll 1
         for (int jc = 0; jc <= j; ++jc) {
             const double* tp = Mb + tidx(j, jc) * TS + a * LB;
             const double* vv = v + jc * LB;
 #pragma unroll
             for (int b = 0; b < LB; ++b) acc += tp[b] * vv[b];
         }
+#pragma unroll 1
         for (int jr = j + 1; jr < S; ++jr) {
             const double* tp = Mb + tidx(jr, j) * TS + a;
             const double* vv = v + jr * LB;
@@ -313,19 +334,17 @@ struct TickLayout {
     static constexpr int o_Wp = o_W + SMAX * 3 * LB;
     static constexpr int o_Vp = o_Wp + SMAX * 3;
     static constexpr int o_Cb = o_Vp + SMAX * 3;
-    static constexpr int o_CC = o_Cb + MAXROWS * LB;   // Cb[k][a]*Cb[k][b], a >= b
-    static constexpr int o_eta = o_CC + MAXROWS * NAB; // active-set threshold weights per row kind
-    static constexpr int o_rb = o_eta + MAXROWS * LB;
+    static constexpr int o_rb = o_Cb + MAXROWS * LB;
     static constexpr int o_ub = o_rb + MAXROWS + 2;
     static constexpr int o_red = o_ub + 8;
     static constexpr int o_int = o_red + 64;
     static constexpr int n_int = 2 * SMAX + 2 * HZ + HZ + 2 * HZ + 2 * SMAX + 16;
     static constexpr int o_bar = ((o_int + (n_int + 1) / 2 + 1) + 1) & ~1;  // mbarriers, 16-byte aligned
-    static constexpr int o_rows = o_bar + 4;           // 6 row arrays (s, lam, d, rp, wc, w), sized at run time
+    static constexpr int o_rows = o_bar + 4;           // 7 row arrays (s, lam, d, rp, wc, w, 1/s), sized at run time
     // rows per array for `mb` inequality rows per block (even, so every array stays 16-byte aligned)
     __host__ __device__ static constexpr int row_stride(int mb) { return (mb * SMAX + 1) & ~1; }
     __host__ __device__ static constexpr int rows_doubles(int mb) {
-        return 6 * row_stride(mb) > PAIRS ? 6 * row_stride(mb) : PAIRS;
+        return 7 * row_stride(mb) > PAIRS ? 7 * row_stride(mb) : PAIRS;
     }
     __host__ __device__ static constexpr size_t bytes(int mb) { return size_t(o_rows + rows_doubles(mb)) * 8; }
 };
@@ -340,8 +359,6 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                                                        double* __restrict__ hscratch) {
     using L = TickLayout<HZ, SMAX, LB>;
     constexpr int E = LB * LB, TS = L::TS, NAB = L::NAB;
-    constexpr int RPT = (MAXROWS * SMAX + NT - 1) / NT;  // inequality rows per thread
-    constexpr int VPT = (LB * SMAX + NT - 1) / NT;       // variables per thread
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x;
 
@@ -363,6 +380,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
     double* r_p = r_d + mrs;
     double* r_c = r_p + mrs;
     double* r_w = r_c + mrs;
+    double* r_is = r_w + mrs;
     double* pairs = sm + L::o_rows;  // alias, assembly only
     double* Nn = sm + L::o_N;
     double* xref = sm + L::o_xref;
@@ -376,8 +394,6 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
     double* Wp = sm + L::o_Wp;
     double* Vp = sm + L::o_Vp;
     double* Cb = sm + L::o_Cb;
-    double* CC = sm + L::o_CC;
-    double* eta = sm + L::o_eta;
     double* rb = sm + L::o_rb;
     double* ub = sm + L::o_ub;
     double* red = sm + L::o_red;
@@ -625,23 +641,8 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                 f6[3] = sg * rotn[1], f6[4] = sg * rotn[4], f6[5] = sg * rotn[7];
             }
             for (int c = 0; c < p.npinned; ++c) rhs -= f6[p.pinned[c]] * p.lo6[p.pinned[c]];
-            double cb[LB];
-            double aa = 0.0;
 #pragma unroll
-            for (int c = 0; c < LB; ++c) {
-                cb[c] = f6[p.comps[c]];
-                Cb[k * LB + c] = cb[c];
-                aa += cb[c] * cb[c];
-            }
-            int ab = 0;
-#pragma unroll
-            for (int a = 0; a < LB; ++a)
-#pragma unroll
-                for (int b = 0; b <= a; ++b) CC[k * NAB + ab++] = cb[a] * cb[b];
-            // weights of the active-set threshold: eta_r = sum_c w_c * diag(Hc)_c
-            const double iaa = 1.0 / fmax(aa * aa, 1e-300);
-#pragma unroll
-            for (int c = 0; c < LB; ++c) eta[k * LB + c] = cb[c] * cb[c] * iaa;
+            for (int c = 0; c < LB; ++c) Cb[k * LB + c] = f6[p.comps[c]];
             rb[k] = rhs;
         }
         gsync<NT>();
@@ -822,16 +823,14 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
 
         // ---- 5. interior point (Mehrotra predictor-corrector + one Gondzio centrality
         //         corrector) to a loose tolerance, then the active-set polish --------------------
-        int rj[RPT], rk[RPT];
-#pragma unroll
-        for (int rr = 0; rr < RPT; ++rr) {
-            const int r = tid + rr * NT;
-            rj[rr] = (r < m) ? r / mb : -1;
-            rk[rr] = (r < m) ? r - (r / mb) * mb : 0;
-        }
-        auto row_dot = [&](int rr, const double* v) {
-            const double* cb = Cb + rk[rr] * LB;
-            const double* vv = v + rj[rr] * LB;
+        const float inv_mb = 1.0f / (float)mb;
+        // row r = j * mb + k: block j, row kind k (exact for these sizes: (r + .5) / mb is never near an integer)
+#define BMPC_FOR_ROWS(r, j, k)                                  \
+    _Pragma("unroll 1") for (int r = tid; r < m; r += NT)       \
+        for (int j = (int)(((float)r + 0.5f) * inv_mb), k = r - j * mb, once_ = 1; once_; once_ = 0)
+        auto cdot = [&](int j, int k, const double* v) {  // (C v)_r
+            const double* cb = Cb + k * LB;
+            const double* vv = v + j * LB;
             double acc = 0.0;
 #pragma unroll
             for (int c = 0; c < LB; ++c) acc += cb[c] * vv[c];
@@ -841,6 +840,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
             const int j = i / LB, c = i - j * LB;
             const double* ww = wr + j * mb;
             double acc = 0.0;
+#pragma unroll 1
             for (int k = 0; k < mb; ++k) acc += Cb[k * LB + c] * ww[k];
             return acc;
         };
@@ -868,18 +868,12 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
 
         for (int i = tid; i < n; i += NT) uv[i] = ub[i % LB];
         double part = 0.0;
-#pragma unroll
-        for (int rr = 0; rr < RPT; ++rr)
-            if (rj[rr] >= 0) {
-                const double* cb = Cb + rk[rr] * LB;
-                double acc = 0.0;
-#pragma unroll
-                for (int c = 0; c < LB; ++c) acc += cb[c] * ub[c];
-                double sl = rb[rk[rr]] - acc;
-                if (!(sl > 1e-3)) sl = 1.0;  // infeasible start for this row: handled through rp
-                r_s[tid + rr * NT] = sl;
-                part += sl;
-            }
+        BMPC_FOR_ROWS(r, j, k) {
+            double sl = rb[k] - cdot(0, k, ub);
+            if (!(sl > 1e-3)) sl = 1.0;  // infeasible start for this row: handled through rp
+            r_s[r] = sl;
+            part += sl;
+        }
         int status = 1, it = 0;
         double mu = 0.0, rdmax = 0.0;
         bool polished = false;
@@ -888,16 +882,13 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
             for (int i = tid; i < n; i += NT) gpart = fmax(gpart, fabs(gv[i]));
             const double gs = 1.0 + gmax<NT>(gpart, red);
             const double mu0 = gsum<NT>(part, red) / (double)m;
-#pragma unroll
-            for (int rr = 0; rr < RPT; ++rr)
-                if (rj[rr] >= 0) r_l[tid + rr * NT] = mu0 / r_s[tid + rr * NT];
+            BMPC_FOR_ROWS(r, j, k) r_l[r] = mu0 / r_s[r];
             gsync<NT>();
 
             double mu_target = p.mu_tol * gs;
             for (int attempt = 0; attempt < 3 && !polished; ++attempt, mu_target *= 1e-2) {
                 // ======================= interior-point iterations =========================
-                bool stop = false;
-                while (!stop) {
+                while (true) {
                     if (it >= p.max_iter) {
                         status = 1;
                         break;
@@ -906,57 +897,46 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     h_need();
                     tile_symv<LB, NT>(Mb, S, uv, gv, tv);  // tv = Hc u + g
                     part = 0.0;
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const int r = tid + rr * NT;
-                            const double s = r_s[r], l = r_l[r];
-                            r_d[r] = l / s;
-                            r_p[r] = row_dot(rr, uv) + s - rb[rk[rr]];
-                            part += s * l;
-                        }
+                    BMPC_FOR_ROWS(r, j, k) {
+                        const double s = r_s[r], l = r_l[r];
+                        const double is = 1.0 / s;
+                        r_is[r] = is;
+                        r_d[r] = l * is;
+                        r_p[r] = cdot(j, k, uv) + s - rb[k];
+                        part += s * l;
+                    }
                     gsync<NT>();
-                    double rd_i[VPT];
                     double rdp = 0.0;
-#pragma unroll
-                    for (int vv = 0; vv < VPT; ++vv) {
-                        const int i = tid + vv * NT;
-                        rd_i[vv] = 0.0;
-                        if (i < n) {
-                            rd_i[vv] = tv[i] + col_gather(i, r_l);
-                            rdp = fmax(rdp, fabs(rd_i[vv]));
-                        }
+#pragma unroll 1
+                    for (int i = tid; i < n; i += NT) {
+                        const double v = tv[i] + col_gather(i, r_l);
+                        tv[i] = v;  // stationarity residual rd
+                        rdp = fmax(rdp, fabs(v));
                     }
                     mu = gsum<NT>(part, red) / (double)m;
                     rdmax = gmax<NT>(rdp, red);
-                    if (mu <= mu_target && rdmax <= 10.0 * mu_target) {
+                    if (mu <= mu_target && rdmax <= p.rd_tol * mu_target) {
                         status = 0;
                         break;
                     }
                     // M = Hc + blockdiag(Cb' diag(d_j) Cb); predictor rhs = -rd - C'(d rp - lam)
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const int r = tid + rr * NT;
-                            r_w[r] = r_d[r] * r_p[r] - r_l[r];
-                        }
+                    BMPC_FOR_ROWS(r, j, k) r_w[r] = r_d[r] * r_p[r] - r_l[r];
+#pragma unroll 1
                     for (int e = tid; e < S * NAB; e += NT) {
                         const int j = e / NAB, ab = e - j * NAB;
-                        const double* dd = r_d + j * mb;
-                        double acc = 0.0;
-                        for (int k = 0; k < mb; ++k) acc += CC[k * NAB + ab] * dd[k];
                         int a = 0, b = ab;  // ab = a(a+1)/2 + b
                         while (b > a) ++a, b -= a;
+                        const double* dd = r_d + j * mb;
+                        double acc = 0.0;
+#pragma unroll 1
+                        for (int k = 0; k < mb; ++k) acc += Cb[k * LB + a] * Cb[k * LB + b] * dd[k];
                         double* dg = Mb + tidx(j, j) * TS;
                         dg[a * LB + b] += acc;
                         if (a != b) dg[b * LB + a] += acc;
                     }
                     gsync<NT>();
-#pragma unroll
-                    for (int vv = 0; vv < VPT; ++vv) {
-                        const int i = tid + vv * NT;
-                        if (i < n) xv[i] = -rd_i[vv] - col_gather(i, r_w);
-                    }
+#pragma unroll 1
+                    for (int i = tid; i < n; i += NT) xv[i] = -tv[i] - col_gather(i, r_w);
                     h_valid = false;
                     gsync<NT>();
                     if (!tile_factor<LB, NT>(Mb, S)) {
@@ -964,150 +944,114 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                         break;
                     }
                     tile_solve<LB, NT>(Mb, S, xv);  // xv = du_aff
-                    double ratio = 0.0;
+                    // affine step: ratio test in FP32 (only a step LENGTH, cut by 0.995 afterwards), and
+                    // mu_aff = mu (1 - a) + a^2 sum(dsa dla) / m   because  s dla + lam dsa = -s lam
+                    float ratio = 0.f;
                     part = 0.0;
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const int r = tid + rr * NT;
-                            const double s = r_s[r], l = r_l[r];
-                            const double dsa = -r_p[r] - row_dot(rr, xv);
-                            const double dla = -l - r_d[r] * dsa;
-                            ratio = fmax(ratio, fmax(-dsa / s, -dla / l));
-                            r_c[r] = dsa * dla;  // second-order term, completed below
-                        }
+                    BMPC_FOR_ROWS(r, j, k) {
+                        const double dsa = -r_p[r] - cdot(j, k, xv);
+                        const double dla = -r_l[r] - r_d[r] * dsa;
+                        ratio = fmaxf(ratio, fmaxf(step_ratio(dsa, r_s[r]), step_ratio(dla, r_l[r])));
+                        r_c[r] = dsa * dla;
+                        part += dsa * dla;
+                    }
+#pragma unroll 1
                     for (int i = tid; i < n; i += NT) duv[i] = xv[i];
-                    ratio = gmax<NT>(ratio, red);
-                    const double a_aff = (ratio > 1.0) ? 1.0 / ratio : 1.0;
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const int r = tid + rr * NT;
-                            const double s = r_s[r], l = r_l[r];
-                            const double dsa = -r_p[r] - row_dot(rr, xv);
-                            const double dla = -l - r_d[r] * dsa;
-                            part += (s + a_aff * dsa) * (l + a_aff * dla);
-                        }
-                    const double mu_aff = gsum<NT>(part, red) / (double)m;
+                    ratio = gmaxf<NT>(ratio, red);
+                    const double a_aff = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
+                    const double mu_aff = mu * (1.0 - a_aff) + a_aff * a_aff * gsum<NT>(part, red) / (double)m;
                     double sigma = mu_aff / mu;
                     sigma = sigma * sigma * sigma;
                     const double tgt = sigma * mu;
                     // corrector: du = du_aff + inv(M) C' wc,  wc = (dsa dla - sigma mu) / s
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const int r = tid + rr * NT;
-                            r_c[r] = (r_c[r] - tgt) / r_s[r];
-                        }
+                    BMPC_FOR_ROWS(r, j, k) r_c[r] = (r_c[r] - tgt) * r_is[r];
                     gsync<NT>();
+#pragma unroll 1
                     for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_c);
                     gsync<NT>();
                     tile_solve<LB, NT>(Mb, S, xv);
+#pragma unroll 1
                     for (int i = tid; i < n; i += NT) duv[i] += xv[i];
                     gsync<NT>();
-                    ratio = 0.0;
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const int r = tid + rr * NT;
-                            const double ds = -r_p[r] - row_dot(rr, duv);
-                            const double dl = -r_l[r] - r_c[r] - r_d[r] * ds;
-                            ratio = fmax(ratio, fmax(-ds / r_s[r], -dl / r_l[r]));
-                        }
-                    ratio = gmax<NT>(ratio, red);
-                    double a2 = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+                    // rows of the combined direction: ds, dlam kept for the passes below
+                    ratio = 0.f;
+                    BMPC_FOR_ROWS(r, j, k) {
+                        const double ds = -r_p[r] - cdot(j, k, duv);
+                        const double dl = -r_l[r] - r_c[r] - r_d[r] * ds;
+                        ratio = fmaxf(ratio, fmaxf(step_ratio(ds, r_s[r]), step_ratio(dl, r_l[r])));
+                        r_p[r] = ds;  // rp is not needed any more this iteration
+                        r_c[r] = dl;
+                    }
+                    ratio = gmaxf<NT>(ratio, red);
+                    double a2 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
                     if (!isfinite(ratio)) {
                         status = 2;
-                        h_issue();
                         break;
                     }
                     // Gondzio centrality corrector: pull outlier products of the trial point into
-                    // [0.1, 10] x target; one more pair of triangular solves with the same factor
+                    // [0.1, 10] x target; one more pair of triangular solves with the same factor.
+                    // Direction change: du += x, ds -= C x, dlam += d (C x) - w,  w = -vt / s
                     if (p.gondzio) {
                         const double at = fmin(1.0, 1.5 * a2 + 0.1);
-#pragma unroll
-                        for (int rr = 0; rr < RPT; ++rr)
-                            if (rj[rr] >= 0) {
-                                const int r = tid + rr * NT;
-                                const double s = r_s[r], l = r_l[r];
-                                const double ds = -r_p[r] - row_dot(rr, duv);
-                                const double dl = -l - r_c[r] - r_d[r] * ds;
-                                const double v = (s + at * ds) * (l + at * dl);
-                                double vt = fmin(fmax(v, 0.1 * tgt), 10.0 * tgt) - v;
-                                vt = fmax(vt, -10.0 * tgt);
-                                r_w[r] = -vt / s;
-                            }
+                        BMPC_FOR_ROWS(r, j, k) {
+                            const double v = (r_s[r] + at * r_p[r]) * (r_l[r] + at * r_c[r]);
+                            double vt = fmin(fmax(v, 0.1 * tgt), 10.0 * tgt) - v;
+                            vt = fmax(vt, -10.0 * tgt);
+                            r_w[r] = -vt * r_is[r];
+                        }
                         gsync<NT>();
+#pragma unroll 1
                         for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_w);
                         gsync<NT>();
                         tile_solve<LB, NT>(Mb, S, xv);
-                        for (int i = tid; i < n; i += NT) xv[i] += duv[i];
-                        gsync<NT>();
-                        ratio = 0.0;
-#pragma unroll
-                        for (int rr = 0; rr < RPT; ++rr)
-                            if (rj[rr] >= 0) {
-                                const int r = tid + rr * NT;
-                                const double ds = -r_p[r] - row_dot(rr, xv);
-                                const double dl = -r_l[r] - (r_c[r] + r_w[r]) - r_d[r] * ds;
-                                ratio = fmax(ratio, fmax(-ds / r_s[r], -dl / r_l[r]));
-                            }
-                        ratio = gmax<NT>(ratio, red);
-                        const double a3 = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+                        ratio = 0.f;
+                        BMPC_FOR_ROWS(r, j, k) {
+                            const double cx = cdot(j, k, xv);
+                            const double ds = r_p[r] - cx;
+                            const double dl = r_c[r] + r_d[r] * cx - r_w[r];
+                            ratio = fmaxf(ratio, fmaxf(step_ratio(ds, r_s[r]), step_ratio(dl, r_l[r])));
+                            r_w[r] = ds;   // candidate direction (own row only)
+                            r_is[r] = dl;
+                        }
+                        ratio = gmaxf<NT>(ratio, red);
+                        const double a3 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
                         if (isfinite(ratio) && a3 > a2) {
                             a2 = a3;
-                            for (int i = tid; i < n; i += NT) duv[i] = xv[i];
-#pragma unroll
-                            for (int rr = 0; rr < RPT; ++rr)
-                                if (rj[rr] >= 0) r_c[tid + rr * NT] += r_w[tid + rr * NT];
-                            gsync<NT>();
+#pragma unroll 1
+                            for (int i = tid; i < n; i += NT) duv[i] += xv[i];
+                            BMPC_FOR_ROWS(r, j, k) r_p[r] = r_w[r], r_c[r] = r_is[r];
                         }
                     }
                     const double alpha = 0.995 * a2;
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const int r = tid + rr * NT;
-                            const double ds = -r_p[r] - row_dot(rr, duv);
-                            const double dl = -r_l[r] - r_c[r] - r_d[r] * ds;
-                            r_s[r] += alpha * ds;
-                            r_l[r] += alpha * dl;
-                        }
-                    gsync<NT>();
+                    BMPC_FOR_ROWS(r, j, k) {
+                        r_s[r] += alpha * r_p[r];
+                        r_l[r] += alpha * r_c[r];
+                    }
+#pragma unroll 1
                     for (int i = tid; i < n; i += NT) uv[i] += alpha * duv[i];
-                    h_issue();  // bring H back while the next iteration starts
+                    h_issue();  // (syncs) bring H back while the next iteration starts
                 }
 
                 // ============================ active-set polish ============================
                 // guess: row active when its barrier weight lam/s dominates the curvature along it
                 for (int j = tid; j < S; j += NT) amask[j] = 0;
                 gsync<NT>();
+                BMPC_FOR_ROWS(r, j, k) {
+                    const double* cb = Cb + k * LB;
+                    const double* hh = hd + j * LB;
+                    double th = 0.0, aa = 0.0;
 #pragma unroll
-                for (int rr = 0; rr < RPT; ++rr)
-                    if (rj[rr] >= 0) {
-                        const int r = tid + rr * NT;
-                        const double* ew = eta + rk[rr] * LB;
-                        const double* hh = hd + rj[rr] * LB;
-                        double th = 0.0;
-#pragma unroll
-                        for (int c = 0; c < LB; ++c) th += ew[c] * hh[c];
-                        if (r_l[r] / r_s[r] > th) atomicOr(&amask[rj[rr]], 1 << rk[rr]);
-                    }
+                    for (int c = 0; c < LB; ++c) th += cb[c] * cb[c] * hh[c], aa += cb[c] * cb[c];
+                    if (r_l[r] * fmax(aa * aa, 1e-300) > th * r_s[r]) atomicOr(&amask[j], 1 << k);
+                }
                 gsync<NT>();
                 bool ok = false;
                 for (int round = 0; round < 4; ++round) {
                     // per block: affine set of the active rows  u_b = p_b + N_b w_b
                     int bad_blk = 0;
                     for (int j = tid; j < S; j += NT) {
-                        double pb[LB], Nb[E];
-#pragma unroll
-                        for (int e = 0; e < E; ++e) Nb[e] = 0.0;
                         int dim = 0;
-                        if (!block_nullspace<LB>(Cb, rb, mb, (unsigned)amask[j], pb, Nb, &dim)) bad_blk = 1;
-#pragma unroll
-                        for (int c = 0; c < LB; ++c) ppv[j * LB + c] = pb[c];
-#pragma unroll
-                        for (int e = 0; e < E; ++e) Nn[j * E + e] = Nb[e];
+                        if (!block_nullspace<LB>(Cb, rb, mb, (unsigned)amask[j], ppv + j * LB, Nn + j * E, &dim)) bad_blk = 1;
                         bdim[j] = dim;
                     }
                     if (gany<NT>(bad_blk)) break;
@@ -1130,28 +1074,26 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                             if (jr * (jr + 1) / 2 > t) --jr;
                             if ((jr + 1) * (jr + 2) / 2 <= t) ++jr;
                             const int jc = t - jr * (jr + 1) / 2;
-                            double hh[E], nn[E], tmp[E];
+                            double hh[E], tmp[E];
                             tile_load<LB>(Mb + t * TS, hh);
-#pragma unroll
-                            for (int e = 0; e < E; ++e) nn[e] = Nn[jc * E + e];
+                            const double* nc = Nn + jc * E;
+                            const double* nr = Nn + jr * E;
 #pragma unroll
                             for (int a = 0; a < LB; ++a)
 #pragma unroll
                                 for (int b = 0; b < LB; ++b) {
                                     double acc = 0.0;
 #pragma unroll
-                                    for (int c = 0; c < LB; ++c) acc += hh[a * LB + c] * nn[c * LB + b];
+                                    for (int c = 0; c < LB; ++c) acc += hh[a * LB + c] * nc[c * LB + b];
                                     tmp[a * LB + b] = acc;
                                 }
 #pragma unroll
-                            for (int e = 0; e < E; ++e) nn[e] = Nn[jr * E + e];
-#pragma unroll
                             for (int a = 0; a < LB; ++a)
 #pragma unroll
                                 for (int b = 0; b < LB; ++b) {
                                     double acc = 0.0;
 #pragma unroll
-                                    for (int c = 0; c < LB; ++c) acc += nn[c * LB + a] * tmp[c * LB + b];
+                                    for (int c = 0; c < LB; ++c) acc += nr[c * LB + a] * tmp[c * LB + b];
                                     hh[a * LB + b] = acc;
                                 }
                             if (jr == jc) {
@@ -1177,16 +1119,14 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     h_issue();  // (syncs) H needed again for the multiplier check
                     // primal check: violated inactive rows join the active set
                     int changed = 0;
-#pragma unroll
-                    for (int rr = 0; rr < RPT; ++rr)
-                        if (rj[rr] >= 0) {
-                            const double bk = rb[rk[rr]];
-                            const double viol = row_dot(rr, upv) - bk;
-                            if (viol > 1e-9 * (1.0 + fabs(bk)) && !((amask[rj[rr]] >> rk[rr]) & 1)) {
-                                atomicOr(&amask[rj[rr]], 1 << rk[rr]);
-                                changed = 1;
-                            }
+                    BMPC_FOR_ROWS(r, j, k) {
+                        const double bk = rb[k];
+                        const double viol = cdot(j, k, upv) - bk;
+                        if (viol > 1e-9 * (1.0 + fabs(bk)) && !((amask[j] >> k) & 1)) {
+                            atomicOr(&amask[j], 1 << k);
+                            changed = 1;
                         }
+                    }
                     if (gany<NT>(changed)) {
                         gsync<NT>();
                         continue;
@@ -1230,6 +1170,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
         } else {
             status = 0;
         }
+#undef BMPC_FOR_ROWS
         gsync<NT>();
 
         // ---- 6. outputs ----------------------------------------------------------------------
