@@ -18,82 +18,175 @@
 
 namespace bmpc {
 
-// Affine set {x : A x = b} of the active rows of one block.  p[LB] particular solution,
-// N[c*LB + a] basis vector a (a < *dim) component c.  false if the rows are inconsistent.
+// ---- normal equations of the active rows of one block, entirely in registers ---------------
+// G = C_A' C_A (LB x LB, PSD) with one right-hand side, reduced by Gauss-Jordan with diagonal
+// pivoting.  The pivot is moved to position `step` by predicated swaps, so every register index
+// is a compile-time constant (no local memory); perm[] maps positions back to components and the
+// first *np positions are the pivots.  A[i][LB] is the transformed right-hand side.
 template <int LB>
-__device__ __noinline__ bool block_nullspace(const double* __restrict__ Cb, const double* __restrict__ rb, int mb, unsigned mask,
-                                double* __restrict__ p, double* __restrict__ N, int* __restrict__ dim_out) {
-    double A[MAXROWS][LB + 1];
-    int k = 0;
-    double scale = 1.0;
+__device__ __forceinline__ void normal_reduce(const double* __restrict__ Cb, int mb, unsigned mask,
+                                              const double (&rhs)[LB], double (&A)[LB][LB + 1], int (&perm)[LB],
+                                              int& np) {
+#pragma unroll
+    for (int a = 0; a < LB; ++a) {
+#pragma unroll
+        for (int b = 0; b < LB; ++b) A[a][b] = 0.0;
+        A[a][LB] = rhs[a];
+        perm[a] = a;
+    }
 #pragma unroll 1
-    for (int r = 0; r < mb; ++r)
-        if ((mask >> r) & 1u) {
-#pragma unroll 1
-            for (int c = 0; c < LB; ++c) {
-                A[k][c] = Cb[r * LB + c];
-                scale = fmax(scale, fabs(A[k][c]));
+    for (int k = 0; k < mb; ++k)
+        if ((mask >> k) & 1u) {
+            double cb[LB];
+#pragma unroll
+            for (int c = 0; c < LB; ++c) cb[c] = Cb[k * LB + c];
+#pragma unroll
+            for (int a = 0; a < LB; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) A[a][b] += cb[a] * cb[b];
+        }
+    double scale = 1e-300;
+#pragma unroll
+    for (int a = 0; a < LB; ++a) {
+        scale = fmax(scale, A[a][a]);
+#pragma unroll
+        for (int b = 0; b < a; ++b) A[b][a] = A[a][b];
+    }
+    np = 0;
+    bool done = false;
+#pragma unroll
+    for (int step = 0; step < LB; ++step) {
+        int pv = step;
+        double best = A[step][step];
+#pragma unroll
+        for (int c = step + 1; c < LB; ++c)
+            if (A[c][c] > best) best = A[c][c], pv = c;
+        const bool take = !done && best > 1e-12 * scale;
+        done = done || !take;
+#pragma unroll
+        for (int c = step + 1; c < LB; ++c) {
+            const bool sw = take && (pv == c);
+#pragma unroll
+            for (int col = 0; col <= LB; ++col) {
+                const double t = A[step][col];
+                A[step][col] = sw ? A[c][col] : t;
+                A[c][col] = sw ? t : A[c][col];
             }
-            A[k][LB] = rb[r];
-            ++k;
+#pragma unroll
+            for (int row = 0; row < LB; ++row) {
+                const double t = A[row][step];
+                A[row][step] = sw ? A[row][c] : t;
+                A[row][c] = sw ? t : A[row][c];
+            }
+            const int tp = perm[step];
+            perm[step] = sw ? perm[c] : tp;
+            perm[c] = sw ? tp : perm[c];
         }
-    unsigned used_r = 0u, used_c = 0u;
-    int prow[LB], pcol[LB], np = 0;
-#pragma unroll 1
-    for (int it = 0; it < LB && it < k; ++it) {
-        double best = 0.0;
-        int br = -1, bc = -1;
-#pragma unroll 1
-        for (int r = 0; r < k; ++r) {
-            if ((used_r >> r) & 1u) continue;
-#pragma unroll 1
-            for (int c = 0; c < LB; ++c)
-                if (!((used_c >> c) & 1u) && fabs(A[r][c]) > best) best = fabs(A[r][c]), br = r, bc = c;
-        }
-        if (best <= 1e-10 * scale) break;
-        used_r |= 1u << br;
-        used_c |= 1u << bc;
-        prow[np] = br, pcol[np] = bc, ++np;
-        const double inv = 1.0 / A[br][bc];
-#pragma unroll 1
-        for (int c = 0; c <= LB; ++c) A[br][c] *= inv;
-#pragma unroll 1
-        for (int r = 0; r < k; ++r) {
-            if (r == br) continue;
-            const double f = A[r][bc];
-            if (f != 0.0)
-#pragma unroll 1
-                for (int c = 0; c <= LB; ++c) A[r][c] -= f * A[br][c];
+        if (take) {
+            const double inv = 1.0 / A[step][step];
+#pragma unroll
+            for (int col = 0; col <= LB; ++col) A[step][col] *= inv;
+#pragma unroll
+            for (int r = 0; r < LB; ++r)
+                if (r != step) {
+                    const double f = A[r][step];
+#pragma unroll
+                    for (int col = 0; col <= LB; ++col) A[r][col] -= f * A[step][col];
+                }
+            ++np;
         }
     }
+}
+
+// Affine set {x : C_A x = b_A} of the active rows of one block: p[LB] particular solution (free
+// components 0), N[c*LB + a] component c of basis vector a (a < *dim_out; unused columns zero).
+// p and N are written with run-time component indices, so they should point to shared memory.
+// false if the rows are inconsistent.
+template <int LB>
+__device__ __noinline__ bool block_nullspace(const double* __restrict__ Cb, const double* __restrict__ rb, int mb,
+                                             unsigned mask, double* __restrict__ p, double* __restrict__ N,
+                                             int* __restrict__ dim_out) {
+    double rhs[LB];
+#pragma unroll
+    for (int c = 0; c < LB; ++c) rhs[c] = 0.0;
     double bmax = 1.0;
 #pragma unroll 1
-    for (int r = 0; r < k; ++r) bmax = fmax(bmax, fabs(A[r][LB]));
+    for (int k = 0; k < mb; ++k)
+        if ((mask >> k) & 1u) {
+            const double bk = rb[k];
+            bmax = fmax(bmax, fabs(bk));
+#pragma unroll
+            for (int c = 0; c < LB; ++c) rhs[c] += Cb[k * LB + c] * bk;
+        }
+    double A[LB][LB + 1];
+    int perm[LB], np;
+    normal_reduce<LB>(Cb, mb, mask, rhs, A, perm, np);
+#pragma unroll
+    for (int e = 0; e < LB * LB; ++e) N[e] = 0.0;
+#pragma unroll
+    for (int i = 0; i < LB; ++i) p[perm[i]] = (i < np) ? A[i][LB] : 0.0;
+#pragma unroll
+    for (int q = 0; q < LB; ++q)
+        if (q >= np) {
+            const int a = q - np;
+#pragma unroll
+            for (int i = 0; i < LB; ++i) N[perm[i] * LB + a] = (i < np) ? -A[i][q] : ((i == q) ? 1.0 : 0.0);
+        }
+    // consistency of the (possibly dependent) active rows
     bool ok = true;
 #pragma unroll 1
-    for (int r = 0; r < k; ++r)
-        if (!((used_r >> r) & 1u) && fabs(A[r][LB]) > 1e-7 * bmax) ok = false;
-#pragma unroll 1
-    for (int c = 0; c < LB; ++c) p[c] = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < np; ++i) p[pcol[i]] = A[prow[i]][LB];
-    int dim = 0;
-#pragma unroll 1
-    for (int c = 0; c < LB; ++c) {
-        if ((used_c >> c) & 1u) continue;
-#pragma unroll 1
-        for (int cc = 0; cc < LB; ++cc) N[cc * LB + dim] = 0.0;
-        N[c * LB + dim] = 1.0;
-#pragma unroll 1
-        for (int i = 0; i < np; ++i) N[pcol[i] * LB + dim] = -A[prow[i]][c];
-        ++dim;
-    }
-#pragma unroll 1
-    for (int c = dim; c < LB; ++c)  // unused basis columns are zero (the caller pads the reduced system)
-#pragma unroll 1
-        for (int cc = 0; cc < LB; ++cc) N[cc * LB + c] = 0.0;
-    *dim_out = dim;
+    for (int k = 0; k < mb; ++k)
+        if ((mask >> k) & 1u) {
+            double acc = -rb[k];
+#pragma unroll
+            for (int i = 0; i < LB; ++i)
+                if (i < np) acc += Cb[k * LB + perm[i]] * A[i][LB];
+            if (fabs(acc) > 1e-7 * bmax) ok = false;
+        }
+    *dim_out = LB - np;
     return ok;
+}
+
+// Fast multiplier check.  With lam the interior-point multipliers of the active rows, the
+// candidate y = lam + C_A z, G z = r - C_A' lam, is the multiplier vector closest to lam that
+// reproduces r = -(gradient) exactly; the interior-point lam sits in the relative interior of the
+// optimal dual face, so y >= 0 whenever the active set is right and strictly complementary.
+// true: y >= 0 and C_A' y = r (certificate holds).  false: undecided, run the exact NNLS check.
+template <int LB>
+__device__ __noinline__ bool block_dual_fast(const double* __restrict__ Cb, int mb, unsigned mask,
+                                             const double* __restrict__ lam, const double* __restrict__ r, double gs) {
+    double rho[LB];
+#pragma unroll
+    for (int c = 0; c < LB; ++c) rho[c] = r[c];
+#pragma unroll 1
+    for (int k = 0; k < mb; ++k)
+        if ((mask >> k) & 1u) {
+            const double lk = lam[k];
+#pragma unroll
+            for (int c = 0; c < LB; ++c) rho[c] -= Cb[k * LB + c] * lk;
+        }
+    double A[LB][LB + 1];
+    int perm[LB], np;
+    normal_reduce<LB>(Cb, mb, mask, rho, A, perm, np);
+    double res[LB];
+#pragma unroll
+    for (int c = 0; c < LB; ++c) res[c] = r[c];
+    bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < mb; ++k)
+        if ((mask >> k) & 1u) {
+            double y = lam[k];
+#pragma unroll
+            for (int i = 0; i < LB; ++i)
+                if (i < np) y += Cb[k * LB + perm[i]] * A[i][LB];
+            if (!(y >= 0.0)) ok = false;
+#pragma unroll
+            for (int c = 0; c < LB; ++c) res[c] -= Cb[k * LB + c] * y;
+        }
+    double rmax = 0.0;
+#pragma unroll
+    for (int c = 0; c < LB; ++c) rmax = fmax(rmax, fabs(res[c]));
+    return ok && rmax <= 1e-9 * gs;
 }
 
 // Is r (= minus the objective gradient restricted to the block) a non-negative combination of

@@ -210,60 +210,103 @@ __device__ __noinline__ bool tile_factor(double* __restrict__ Mb, int S) {
         }
         gsync<NT>();
     }
+    // Solve form: M = Lh D Lh' with Lh unit block-lower, so every substitution step is ONE phase.
+    // Lh(jr,jc) = L(jr,jc) inv(L(jc,jc));  the diagonal tile becomes inv(D_j) = inv(L_jj)' inv(L_jj).
+    const int nlow = S * (S - 1) / 2;
+    for (int t = tid; t < nlow; t += NT) {
+        int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        if (r * (r + 1) / 2 > t) --r;
+        if ((r + 1) * (r + 2) / 2 <= t) ++r;
+        const int jc = t - r * (r + 1) / 2, jr = r + 1;  // strictly lower tiles
+        double* tp = Mb + tidx(jr, jc) * TS;
+        double a[E], li[E], o[E];
+        tile_load<LB>(tp, a);
+        tile_load<LB>(Mb + tidx(jc, jc) * TS, li);
+#pragma unroll
+        for (int x = 0; x < LB; ++x)
+#pragma unroll
+            for (int y = 0; y < LB; ++y) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = y; k < LB; ++k) v += a[x * LB + k] * li[k * LB + y];
+                o[x * LB + y] = v;
+            }
+        tile_store<LB>(tp, o);
+    }
+    gsync<NT>();
+    for (int j = tid; j < S; j += NT) {
+        double* tp = Mb + tidx(j, j) * TS;
+        double li[E], o[E];
+        tile_load<LB>(tp, li);
+#pragma unroll
+        for (int x = 0; x < LB; ++x)
+#pragma unroll
+            for (int y = 0; y < LB; ++y) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = (x > y ? x : y); k < LB; ++k) v += li[k * LB + x] * li[k * LB + y];
+                o[x * LB + y] = v;
+            }
+        tile_store<LB>(tp, o);
+    }
+    gsync<NT>();
     return ok;
 }
 
-// x <- inv(L L') x with the factor of tile_factor.  x has LB*S entries in shared memory.
-template <int LB, int NT>
+// x <- inv(M) x with the factor of tile_factor (unit block-lower Lh below the diagonal, inv(D_j)
+// on it).  x has LB*S entries in shared memory.  One group barrier per block step.
+template <int LB, int NT, int NPT>
 __device__ __noinline__ void tile_solve(const double* __restrict__ Mb, int S, double* __restrict__ x) {
     constexpr int TS = TileT<LB>::TS;
     const int tid = threadIdx.x;
-    // forward: y_j = Li_j (x_j - sum_{p<j} L(j,p) y_p), column oriented
-    for (int jc = 0; jc < S; ++jc) {
-        double yj = 0.0;
-        if (tid < LB) {
-            const double* li = Mb + tidx(jc, jc) * TS + tid * LB;
-            const double* xj = x + jc * LB;
-#pragma unroll
-            for (int b = 0; b < LB; ++b)
-                if (b <= tid) yj += li[b] * xj[b];
-        }
-        gsync<NT>();
-        if (tid < LB) x[jc * LB + tid] = yj;
-        gsync<NT>();
+    const int n = S * LB;
+    // forward: z_jr -= Lh(jr,jc) z_jc for jr > jc
+    for (int jc = 0; jc + 1 < S; ++jc) {
+        const double* zc = x + jc * LB;
         const int cnt = (S - 1 - jc) * LB;
+#pragma unroll 1
         for (int t = tid; t < cnt; t += NT) {
             const int r = t / LB, a = t - r * LB;
             const double* lt = Mb + tidx(jc + 1 + r, jc) * TS + a * LB;
-            const double* yv = x + jc * LB;
             double acc = 0.0;
 #pragma unroll
-            for (int b = 0; b < LB; ++b) acc += lt[b] * yv[b];
+            for (int b = 0; b < LB; ++b) acc += lt[b] * zc[b];
             x[(jc + 1 + r) * LB + a] -= acc;
         }
         gsync<NT>();
     }
-    // backward: x_j = Li_j' (y_j - sum_{p>j} L(p,j)' x_p), column oriented
-    for (int jc = S - 1; jc >= 0; --jc) {
-        double xj = 0.0;
-        if (tid < LB) {
-            const double* li = Mb + tidx(jc, jc) * TS;
-            const double* yv = x + jc * LB;
+    // middle: w_j = inv(D_j) z_j
+    {
+        double w[NPT];
 #pragma unroll
-            for (int b = 0; b < LB; ++b)
-                if (b >= tid) xj += li[b * LB + tid] * yv[b];
+        for (int q = 0; q < NPT; ++q) {
+            const int i = tid + q * NT;
+            w[q] = 0.0;
+            if (i < n) {
+                const int j = i / LB, a = i - j * LB;
+                const double* di = Mb + tidx(j, j) * TS + a * LB;
+                const double* zj = x + j * LB;
+#pragma unroll
+                for (int b = 0; b < LB; ++b) w[q] += di[b] * zj[b];
+            }
         }
         gsync<NT>();
-        if (tid < LB) x[jc * LB + tid] = xj;
+#pragma unroll
+        for (int q = 0; q < NPT; ++q)
+            if (tid + q * NT < n) x[tid + q * NT] = w[q];
         gsync<NT>();
+    }
+    // backward: x_r -= Lh(jc,r)' x_jc for r < jc
+    for (int jc = S - 1; jc > 0; --jc) {
+        const double* xc = x + jc * LB;
         const int cnt = jc * LB;
+#pragma unroll 1
         for (int t = tid; t < cnt; t += NT) {
-            const int r = t / LB, a = t - r * LB;  // block row r < jc, component a
+            const int r = t / LB, a = t - r * LB;
             const double* lt = Mb + tidx(jc, r) * TS + a;
-            const double* xv = x + jc * LB;
             double acc = 0.0;
 #pragma unroll
-            for (int b = 0; b < LB; ++b) acc += lt[b * LB] * xv[b];
+            for (int b = 0; b < LB; ++b) acc += lt[b * LB] * xc[b];
             x[r * LB + a] -= acc;
         }
         gsync<NT>();
@@ -359,6 +402,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                                                        double* __restrict__ hscratch) {
     using L = TickLayout<HZ, SMAX, LB>;
     constexpr int E = LB * LB, TS = L::TS, NAB = L::NAB;
+    constexpr int NPT = (LB * SMAX + NT - 1) / NT;  // variables per thread
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x;
 
@@ -943,7 +987,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                         status = 2;
                         break;
                     }
-                    tile_solve<LB, NT>(Mb, S, xv);  // xv = du_aff
+                    tile_solve<LB, NT, NPT>(Mb, S, xv);  // xv = du_aff
                     // affine step: ratio test in FP32 (only a step LENGTH, cut by 0.995 afterwards), and
                     // mu_aff = mu (1 - a) + a^2 sum(dsa dla) / m   because  s dla + lam dsa = -s lam
                     float ratio = 0.f;
@@ -969,7 +1013,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_c);
                     gsync<NT>();
-                    tile_solve<LB, NT>(Mb, S, xv);
+                    tile_solve<LB, NT, NPT>(Mb, S, xv);
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) duv[i] += xv[i];
                     gsync<NT>();
@@ -1003,7 +1047,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
 #pragma unroll 1
                         for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_w);
                         gsync<NT>();
-                        tile_solve<LB, NT>(Mb, S, xv);
+                        tile_solve<LB, NT, NPT>(Mb, S, xv);
                         ratio = 0.f;
                         BMPC_FOR_ROWS(r, j, k) {
                             const double cx = cdot(j, k, xv);
@@ -1108,7 +1152,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     h_valid = false;
                     gsync<NT>();
                     if (!tile_factor<LB, NT>(Mb, S)) break;
-                    tile_solve<LB, NT>(Mb, S, xv);
+                    tile_solve<LB, NT, NPT>(Mb, S, xv);
                     for (int i = tid; i < n; i += NT) {
                         const int j = i / LB, c = i - j * LB;
                         double acc = ppv[i];
@@ -1141,6 +1185,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
 #pragma unroll
                         for (int c = 0; c < LB; ++c) rneg[c] = -tv[j * LB + c];
                         unsigned drop = 0u;
+                        if (block_dual_fast<LB>(Cb, mb, (unsigned)amask[j], r_l + j * mb, rneg, gs)) continue;
                         if (!block_dual_check<LB>(Cb, mb, (unsigned)amask[j], rneg, gs, &drop)) {
                             if (drop == 0u) fail = 1;
                             else amask[j] &= ~(int)drop, changed = 1;
