@@ -56,7 +56,7 @@ def workload_config(batch, n_gpus):
 # ------------------------------------------------------------------------------------------
 # algorithmic FLOPs (DESIGN.md "FLOP model"): 2 per FMA, mathematically required work only
 # ------------------------------------------------------------------------------------------
-def flops_per_solve(S, iters, LB=5, mb=11, h=10, stages=None):
+def flops_per_solve(S, iters, LB=5, mb=11, h=10, stages=None, polish_rounds=1.15):
     n, m = LB * S, mb * S
     if stages is None:  # walking: one block per stage; standing: two per stage
         per_stage = max(1, round(S / h))
@@ -67,8 +67,11 @@ def flops_per_solve(S, iters, LB=5, mb=11, h=10, stages=None):
             sr = stages[jr]
             f_setup += (h - 1 - sr) * (2 * 2 * 9 * LB + 2 * 3 * LB * LB) + 2 * 3 * LB * LB
     f_setup += S * h * 40.0
-    f_iter = n ** 3 / 3.0 + 6.0 * n * n + m * (8.0 * LB + 20.0) + S * mb * LB * (LB + 1.0)
-    return f_setup + iters * f_iter + 600.0
+    # one Cholesky, Hc u, three solve pairs (predictor, corrector, Gondzio), row passes, block-diagonal update
+    f_iter = n ** 3 / 3.0 + 8.0 * n * n + m * (8.0 * LB + 20.0) + S * mb * LB * (LB + 1.0)
+    # polish round: one factorisation, two Hc products, one solve pair, null-space transform of every tile
+    f_polish = n ** 3 / 3.0 + 8.0 * n * n + 4.0 * LB ** 3 * S * (S + 1) / 2.0
+    return f_setup + iters * f_iter + (polish_rounds * f_polish if S > 0 else 0.0) + 600.0
 
 
 def batch_flops(contact, iters):
@@ -227,8 +230,8 @@ def run_b200(args, rank, local_rank, world):
     fl = batch_flops(batch["contact"], iters)
     peaks = measure(local_rank)
     kernels = []
-    for cls, name in ((0, "mpc_tick_kernel<10,10,5,128> (<=10 stance foot-stages: walking)"),
-                      (1, "mpc_tick_kernel<10,20,5,256> (11..20 stance foot-stages: standing)")):
+    for cls, name in ((0, "mpc_tick2_kernel<10,10,5,32> (<=10 stance foot-stages: walking class, one warp per robot)"),
+                      (1, "mpc_tick2_kernel<10,20,5,128> (11..20 stance foot-stages: standing class, one CTA per robot)")):
         ach = fl[cls] / (kt[1 + cls] * 1e-3) / 1e12 if kt[1 + cls] > 0 else 0.0
         kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
                         "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"]})
@@ -259,14 +262,8 @@ def run_b200(args, rank, local_rank, world):
            "api": "BatchedMPC.pinned_tick(n).run(): pinned host -> device, bmpc_step, device -> pinned host, sync"}
 
     # ---- stats reduction (the only collective): NCCL sum / max over ranks --------------------
-    stats_sum = torch.tensor([float(n), float(iters.sum()), float((status != 0).sum()), float((status == 3).sum())],
-                             dtype=torch.float64, device=dev)
-    stats_max = torch.tensor([float(iters.max()), float(resid[:, 0].max()), float(resid[:, 1].max())],
-                             dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats_sum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(stats_max, op=dist.ReduceOp.MAX)
-    ssum, smax = stats_sum.cpu().numpy(), stats_max.cpu().numpy()
+    from biped_mpc_py_b200.shard import local_stats, reduce_stats
+    stats = reduce_stats(*local_stats(status, iters, resid), device=dev)
 
     line = None
     if rank == 0:
@@ -294,9 +291,10 @@ def run_b200(args, rank, local_rank, world):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "latency": latency,
-                "solver": {"mean_iters": float(ssum[1] / ssum[0]), "max_iters": int(smax[0]),
-                           "not_optimal": int(ssum[2]), "bad_input": int(ssum[3]), "max_mu": float(smax[1]),
-                           "max_rd": float(smax[2]), "instances": int(ssum[0])}}
+                "solver": {"mean_iters": float(stats["mean_iters"]), "max_iters": int(stats["iters_max"]),
+                           "not_optimal": int(stats["not_optimal"]), "bad_input": int(stats["bad_input"]),
+                           "max_mu": float(stats["mu_max"]), "max_rd": float(stats["rd_max"]),
+                           "instances": int(stats["instances"])}}
         print(json.dumps(line), flush=True)
     solver.close()
     if world > 1:

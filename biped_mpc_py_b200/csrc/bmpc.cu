@@ -11,7 +11,7 @@
 #include <string>
 
 #include "../../include/biped_mpc_b200.h"
-#include "bmpc_solve.cuh"
+#include "bmpc_small.cuh"
 #include "bmpc_tick.cuh"
 
 using namespace bmpc;

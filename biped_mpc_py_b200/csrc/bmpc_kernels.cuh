@@ -1,22 +1,9 @@
-// Batched HECTOR-style force-and-moment MPC for sm_100a: device code.
+// Batched HECTOR-style force-and-moment MPC for sm_100a: shared device definitions.
 //
-// One CTA solves one robot's MPC tick end to end:
-//   1. stage inputs into shared memory with TMA bulk copies (cp.async.bulk + mbarrier),
-//      prefetching the next instance while the current one is solved;
-//   2. build the discretised single-rigid-body model over the horizon and the
-//      CONTACT-REDUCED CONDENSED QP  min 1/2 u'Hc u + g'u,  Cb u_b <= rb per block
-//      (reference: MPC.py:61-109 references, 148-185 dynamics, 202-286 QP data);
-//   3. solve it with a Mehrotra predictor-corrector interior-point method in FP64,
-//      the packed Cholesky factor of  Hc + C' diag(lam/s) C  resident in shared memory
-//      (replaces cvxopt.solvers.qp, MPC.py:289-297);
-//   4. map the first-stage forces/moments to joint torques (MPC.py:306-365, 426-470).
-//
-// Why these choices (measured): the QP is strictly convex but nearly flat
-// in the forces (R = 1e-4 vs Q up to 700, cond(Hc) ~ 1e6), so first-order splitting
-// (ADMM/OSQP) needs thousands of iterations to place the forces, while the interior
-// point method reaches 1e-7 relative in ~13 iterations.  Every instance has its own
-// 50..120-variable matrix and a single right-hand side, so there is no GEMM to put on
-// tcgen05; the work is FP64 CUDA-core FMA fed from shared memory.
+// Parameter / pointer structs passed to the kernels, TMA + mbarrier helpers, small 3x3 algebra,
+// and the closed-form kinematics of the reference (rotation MPC.py:111-138, leg Jacobian
+// MPC.py:306-365, swing PD + torque map MPC.py:426-470, foot position MPC.py:367-404).
+// The fused tick kernel is in bmpc_tick.cuh, its active-set polish in bmpc_polish.cuh.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -65,8 +52,6 @@ struct IoPtrs {
 // ------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // j <= i
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -96,31 +81,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-template <int NT>
-__device__ __forceinline__ double block_sum(double v, double* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) t += red[w];
-    __syncthreads();
-    return t;
-}
-template <int NT>
-__device__ __forceinline__ double block_max(double v, double* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = red[0];
-#pragma unroll
-    for (int w = 1; w < NT / 32; ++w) t = fmax(t, red[w]);
-    __syncthreads();
-    return t;
 }
 
 __device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* c) {
@@ -165,112 +125,6 @@ __device__ __forceinline__ void eul2rotm(const double* e, double* R) {
     R[6] = -sp;
     R[7] = cp * sr;
     R[8] = cp * cr;
-}
-
-// ------------------------------------------------------------------------------------
-// shared-memory layout (offsets in doubles), sized on the host with the same formulas
-// ------------------------------------------------------------------------------------
-template <int HZ, int SMAX, int LB>
-struct Layout {
-    static constexpr int N = LB * SMAX;              // reduced variables (max)
-    static constexpr int HP = N * (N + 1) / 2;       // packed lower triangle of Hc
-    static constexpr int MP = (N + 1) * (N + 2) / 2; // packed factor incl. the augmented rhs row
-    static constexpr int MR = MAXROWS * SMAX;
-    static constexpr int NV = ((N + 1) + 3) & ~3;    // padded vector length
-    static constexpr int o_in = 0;                   // 2 x IN_DOUBLES (TMA destinations)
-    static constexpr int o_cur = o_in + 2 * IN_DOUBLES;
-    static constexpr int o_xref = o_cur + IN_DOUBLES;
-    static constexpr int o_rinv = o_xref + HZ * 12;
-    static constexpr int o_psum = o_rinv + HZ * 9;
-    static constexpr int o_iwinv = o_psum + HZ * 9;
-    static constexpr int o_err = o_iwinv + HZ * 9;
-    static constexpr int o_footv = o_err + HZ * 12;   // 3 variants x 6
-    static constexpr int o_rot = o_footv + 24;        // current-orientation rotation (9) + pad
-    static constexpr int o_W = o_rot + 12;            // SMAX x 3 x LB
-    static constexpr int o_Wp = o_W + SMAX * 3 * LB;  // SMAX x 3 (pinned components -> omega)
-    static constexpr int o_Vp = o_Wp + SMAX * 3;      // SMAX x 3 (pinned components -> velocity)
-    static constexpr int o_Cb = o_Vp + SMAX * 3;      // MAXROWS x LB
-    static constexpr int o_rb = o_Cb + MAXROWS * LB;  // MAXROWS
-    static constexpr int o_ub = o_rb + MAXROWS + 2;   // LB start point (+pad)
-    static constexpr int o_H = o_ub + 8;
-    static constexpr int o_M = o_H + HP;
-    static constexpr int o_g = o_M + MP;
-    static constexpr int o_u = o_g + NV;
-    static constexpr int o_du = o_u + NV;
-    static constexpr int o_x = o_du + NV;    // rhs / solution vector of the triangular solves
-    static constexpr int o_t = o_x + NV;     // H*u
-    static constexpr int o_inv = o_t + NV;   // 1 / L_kk
-    static constexpr int o_wrow = o_inv + NV;  // row vector being gathered by C'
-    static constexpr int o_drow = o_wrow + MR; // lam / s
-    static constexpr int o_red = o_drow + MR;  // reduction scratch (32) + misc scalars (32)
-    static constexpr int o_int = o_red + 64;   // ints from here
-    static constexpr int n_int = 2 * SMAX + 2 * HZ + HZ + 2 * HZ + 16;  // blk_stage, blk_foot, blockOf, footsel, contact
-    static constexpr int o_bar = o_int + (n_int + 1) / 2 + 2;  // two mbarriers (8-byte aligned)
-    static constexpr int total_doubles = o_bar + 2;
-    static constexpr size_t bytes = size_t(total_doubles) * 8;
-};
-
-// ------------------------------------------------------------------------------------
-// packed Cholesky of the (n+1)-row augmented matrix: rows 0..n-1 are M (lower, packed),
-// row n holds a right-hand side; after the call row n holds L^{-1} rhs (forward
-// substitution for free) and inv[k] = 1/L_kk.  Returns false on a non-positive pivot.
-// ------------------------------------------------------------------------------------
-template <int NT>
-__device__ bool chol_aug(double* M, int n, double* inv) {
-    constexpr int TX = 8, TY = NT / 8;
-    const int tid = threadIdx.x;
-    const int tx = tid & (TX - 1), ty = tid / TX;
-    bool ok = true;
-    for (int k = 0; k < n; ++k) {
-        const double mkk = M[tri(k, k)];
-        if (!(mkk > 0.0) || !isfinite(mkk)) {  // uniform: every thread reads the same value
-            ok = false;
-            break;
-        }
-        const double ik = rsqrt(mkk);
-        for (int i = k + 1 + tid; i <= n; i += NT) M[tri(i, k)] *= ik;
-        if (tid == 0) inv[k] = ik;
-        __syncthreads();
-        for (int i = k + 1 + ty; i <= n; i += TY) {
-            const double lik = M[tri(i, k)];
-            double* row = M + tri(i, 0);
-            const int jend = (i < n) ? i : n - 1;  // augmented row has no diagonal
-            for (int j = k + 1 + tx; j <= jend; j += TX) row[j] -= lik * M[tri(j, k)];
-        }
-        __syncthreads();
-    }
-    return ok;
-}
-
-// x <- L^{-T} x   (x has n entries, one per thread; block-wide, one barrier per step)
-template <int NT>
-__device__ void solve_backward(const double* M, int n, const double* inv, double* x) {
-    const int tid = threadIdx.x;
-    double bi = (tid < n) ? x[tid] : 0.0;
-    for (int k = n - 1; k >= 0; --k) {
-        if (tid == k) {
-            bi *= inv[k];
-            x[k] = bi;
-        }
-        __syncthreads();
-        if (tid < k) bi -= M[tri(k, tid)] * x[k];
-    }
-    __syncthreads();
-}
-// x <- L^{-1} x
-template <int NT>
-__device__ void solve_forward(const double* M, int n, const double* inv, double* x) {
-    const int tid = threadIdx.x;
-    double bi = (tid < n) ? x[tid] : 0.0;
-    for (int k = 0; k < n; ++k) {
-        if (tid == k) {
-            bi *= inv[k];
-            x[k] = bi;
-        }
-        __syncthreads();
-        if (tid > k && tid < n) bi -= M[tri(tid, k)] * x[k];
-    }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------

@@ -341,17 +341,4 @@ __device__ __noinline__ bool block_dual_check(const double* __restrict__ Cb, int
     return false;
 }
 
-// y = Hc x + add  for the packed symmetric Hc (one row per thread); result in out[]
-__device__ __forceinline__ void symv_packed(const double* __restrict__ Hp, int n, const double* __restrict__ x,
-                                            const double* __restrict__ add, double* __restrict__ out) {
-    const int tid = threadIdx.x;
-    if (tid < n) {
-        double acc = add ? add[tid] : 0.0;
-        const double* row = Hp + tri(tid, 0);
-        for (int j = 0; j <= tid; ++j) acc += row[j] * x[j];
-        for (int j = tid + 1; j < n; ++j) acc += Hp[tri(j, tid)] * x[j];
-        out[tid] = acc;
-    }
-}
-
 }  // namespace bmpc

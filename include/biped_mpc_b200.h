@@ -48,19 +48,19 @@ typedef struct bmpc_params {
     double hip_offset[3];  /* MPC.py:43 (used by bmpc_foot_positions only) */
     double mu;             /* MPC.py:44 */
     double f_max[3], f_min[3], tau_max[3], tau_min[3]; /* MPC.py:45-48 */
-    /* interior-point options (0 selects the default in brackets) */
-    int32_t max_iter;      /* [40] */
-    int32_t polish;        /* reserved */
-    double mu_tol;         /* [1e-12] complementarity target, objective = reference / 2 */
-    double rd_tol;         /* [1e-9]  stationarity residual (inf-norm)                    */
+    /* solver options (0 selects the default in brackets) */
+    int32_t max_iter;      /* [40] interior-point iteration cap                                    */
+    int32_t polish;        /* reserved (the active-set polish is always on)                        */
+    double mu_tol;         /* [1e-7] complementarity mu <= mu_tol*(1+|g|inf) hands over to the polish */
+    double rd_tol;         /* [10]   stationarity residual <= rd_tol * that mu target               */
 } bmpc_params;
 
 typedef struct bmpc_handle bmpc_handle;
 
 /* status[] values written per instance */
-#define BMPC_STATUS_OPTIMAL   0   /* converged to mu_tol / rd_tol                        */
+#define BMPC_STATUS_OPTIMAL   0   /* exact optimum: active-set polish certified (KKT)    */
 #define BMPC_STATUS_MAXITER   1   /* iteration cap hit; best iterate returned            */
-#define BMPC_STATUS_NUMERIC   2   /* factorisation broke down near the optimum; iterate returned */
+#define BMPC_STATUS_NUMERIC   2   /* factorisation broke down and the polish did not certify; iterate returned */
 #define BMPC_STATUS_BADINPUT  3   /* NaN/Inf in inputs or pitch = +-pi/2 (MPC.py:160-164 singular) */
 
 /* Create a solver bound to `device` for batches up to `max_batch`.  Replaces the
@@ -76,7 +76,7 @@ int bmpc_destroy(bmpc_handle* h);
  *        pf_w[N,6]
  *   out: controls[N,h,12]  states[N,h,13] (nullable)  tau[N,10]  status[N]  iters[N]
  *        fric_active[N,h] (nullable; bit 4*leg+r = friction row r of MPC.py:220-229 active)
- *        resid[N,2] (nullable; final complementarity mu and stationarity residual) */
+ *        resid[N,2] (nullable; complementarity mu - 0 once polished - and the last stationarity residual) */
 int bmpc_step(bmpc_handle* h, int n,
               const double* x_fb, const int32_t* phase_k, const double* t_swing,
               const double* foot, const uint8_t* contact,
