@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -36,7 +37,8 @@ struct Variant {
     TickKernel fn = nullptr;
     size_t smem = 0;
     int threads = 0;
-    int resident = 0;  // CTAs that fit on the device at once
+    int per_cta = 1;   // robots (thread groups) per CTA
+    int resident = 0;  // thread groups that fit on the device at once
     size_t scratch_doubles = 0;  // per resident CTA: one copy of the tile matrix H
     double* d_scratch = nullptr;
 };
@@ -79,7 +81,9 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     d.mu_tol = P.mu_tol > 0 ? P.mu_tol : 1e-7;
     d.rd_tol = P.rd_tol > 0 ? P.rd_tol : 10.0;
     d.gondzio = 1;
-    d.init_fz_frac = 0.1;
+    d.init_fz_frac = 0.2;   // start point: 20 % of the fz range, friction/moment components centred
+    d.mu0_scale = 0.1;      // initial complementarity = mu0_scale * mean slack
+    d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
     memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));
     memcpy(d.Q, P.Q, sizeof(d.Q));
     memcpy(d.R, P.R, sizeof(d.R));
@@ -142,18 +146,19 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     return 0;
 }
 
-template <int HZ, int SMAX, int LB, int NT>
+template <int HZ, int SMAX, int LB, int NT, int NW>
 int setup_variant(Variant& v, int num_sms, int mb) {
     using L = TickLayout<HZ, SMAX, LB>;
-    v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT>;
-    v.smem = L::bytes(mb);
-    v.threads = NT;
-    v.scratch_doubles = L::MB;
+    v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT, NW>;
+    v.smem = L::bytes(mb) * NW + 16;  // + the CTA-wide lockstep mbarrier
+    v.threads = NT * NW;
+    v.per_cta = NW;
+    v.scratch_doubles = L::g_total;
     CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, NT, v.smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, NT * NW, v.smem));
     if (per_sm < 1) return fail("kernel does not fit on an SM");
-    v.resident = per_sm * num_sms;
+    v.resident = per_sm * num_sms * NW;
     CUDA_TRY(cudaMalloc(&v.d_scratch, sizeof(double) * v.scratch_doubles * (size_t)v.resident));
     return 0;
 }
@@ -170,8 +175,8 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
     for (int b = 0; b < 2; ++b) {
         const Variant& v = h->bucket[b];
-        // persistent CTAs: as many as fit on the device, each strides over its bucket's work list
-        const int grid = std::min(n, v.resident);
+        // persistent thread groups: as many as fit on the device, each strides over its bucket's work list
+        const int grid = (std::min(n, v.resident) + v.per_cta - 1) / v.per_cta;
         v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b,
                                                v.d_scratch);
         if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2 + b], st));
@@ -209,12 +214,22 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         return 1;
     }
     int rc = 0;
+    // experiment knobs (threads per robot in each class); the defaults are the shipped configuration
+    const char* ew = getenv("BMPC_NW_WALK");
+    const char* es = getenv("BMPC_NT_STAND");
+    const int nww = ew ? atoi(ew) : 5, nts = es ? atoi(es) : 128;  // walking: robots per CTA; standing: threads per robot
     if (h->dp.LB == 5) {
-        rc = setup_variant<10, 10, 5, 32>(h->bucket[0], h->num_sms, h->dp.mb) ||
-             setup_variant<10, 20, 5, 128>(h->bucket[1], h->num_sms, h->dp.mb);
+        rc = (nww == 1 ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
+              : nww == 2 ? setup_variant<10, 10, 5, 32, 2>(h->bucket[0], h->num_sms, h->dp.mb)
+              : nww == 3 ? setup_variant<10, 10, 5, 32, 3>(h->bucket[0], h->num_sms, h->dp.mb)
+              : nww == 4 ? setup_variant<10, 10, 5, 32, 4>(h->bucket[0], h->num_sms, h->dp.mb)
+              : nww == 5 ? setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)
+                         : setup_variant<10, 10, 5, 32, 10>(h->bucket[0], h->num_sms, h->dp.mb)) ||
+             (nts == 256 ? setup_variant<10, 20, 5, 256, 1>(h->bucket[1], h->num_sms, h->dp.mb)
+                         : setup_variant<10, 20, 5, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb));
     } else {
-        rc = setup_variant<10, 10, 6, 32>(h->bucket[0], h->num_sms, h->dp.mb) ||
-             setup_variant<10, 20, 6, 128>(h->bucket[1], h->num_sms, h->dp.mb);
+        rc = setup_variant<10, 10, 6, 32, 4>(h->bucket[0], h->num_sms, h->dp.mb) ||
+             setup_variant<10, 20, 6, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb);
     }
     if (rc) {
         delete h;

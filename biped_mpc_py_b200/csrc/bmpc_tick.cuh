@@ -157,7 +157,7 @@ __device__ __forceinline__ bool tile_chol_inv(const double (&a)[LB * LB], double
 template <int LB, int NT>
 __device__ __noinline__ bool tile_factor(double* __restrict__ Mb, int S) {
     constexpr int E = LB * LB, TS = TileT<LB>::TS;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (NT - 1);
     bool ok = true;
     for (int jc = 0; jc < S; ++jc) {
         double li[E];
@@ -258,7 +258,7 @@ __device__ __noinline__ bool tile_factor(double* __restrict__ Mb, int S) {
 template <int LB, int NT, int NPT>
 __device__ __noinline__ void tile_solve(const double* __restrict__ Mb, int S, double* __restrict__ x) {
     constexpr int TS = TileT<LB>::TS;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (NT - 1);
     const int n = S * LB;
     // forward: z_jr -= Lh(jr,jc) z_jc for jr > jc
     for (int jc = 0; jc + 1 < S; ++jc) {
@@ -319,7 +319,7 @@ __device__ __noinline__ void tile_symv(const double* __restrict__ Mb, int S, con
                           const double* __restrict__ add, double* __restrict__ out) {
     constexpr int TS = TileT<LB>::TS;
     const int n = S * LB;
-    for (int i = threadIdx.x; i < n; i += NT) {
+    for (int i = threadIdx.x & (NT - 1); i < n; i += NT) {
         const int j = i / LB, a = i - j * LB;
         double acc = add ? add[i] : 0.0;
 #pragma unroll 1
@@ -350,73 +350,86 @@ struct TickLayout {
     static constexpr int NTILE = SMAX * (SMAX + 1) / 2;
     static constexpr int MB = NTILE * TS;              // tile matrix (H, then the factor, in place)
     static constexpr int NV = (N + 3) & ~3;
-    static constexpr int MR = MAXROWS * SMAX;
     static constexpr int NPAIR = HZ * (HZ + 1) / 2;
     static constexpr int NAB = LB * (LB + 1) / 2;
+    // ---- shared memory ----
     static constexpr int o_M = 0;
-    static constexpr int o_in = o_M + MB;              // 2 x IN_DOUBLES TMA destinations
-    static constexpr int o_cur = o_in + 2 * IN_DOUBLES;
-    static constexpr int o_g = o_cur + IN_DOUBLES;
+    static constexpr int o_in = o_M + MB;              // 2 x IN_DOUBLES TMA destinations (inputs, double buffered)
+    static constexpr int o_g = o_in + 2 * IN_DOUBLES;
     static constexpr int o_u = o_g + NV;
-    static constexpr int o_du = o_u + NV;
-    static constexpr int o_x = o_du + NV;
-    static constexpr int o_t = o_x + NV;               // H u, gradients
-    static constexpr int o_hd = o_t + NV;              // diag(Hc)
-    static constexpr int o_up = o_hd + NV;             // polished point
-    static constexpr int o_pp = o_up + NV;             // polish: particular solution
-    static constexpr int PAIRS = NPAIR * 10;           // assembly scratch aliased onto the row arrays
-    static constexpr int o_N = o_pp + NV;              // polish: null-space blocks SMAX x LB x LB
-    static constexpr int o_xref = o_N + SMAX * LB * LB;
-    static constexpr int o_rinv = o_xref + HZ * 12;
-    static constexpr int o_psum = o_rinv + HZ * 9;
-    static constexpr int o_iwinv = o_psum + HZ * 9;
-    static constexpr int o_err = o_iwinv + HZ * 9;
-    static constexpr int o_footv = o_err + HZ * 12;
-    static constexpr int o_rot = o_footv + 24;
-    static constexpr int o_W = o_rot + 12;
-    static constexpr int o_Wp = o_W + SMAX * 3 * LB;
-    static constexpr int o_Vp = o_Wp + SMAX * 3;
-    static constexpr int o_Cb = o_Vp + SMAX * 3;
+    static constexpr int o_Cb = o_u + NV;
     static constexpr int o_rb = o_Cb + MAXROWS * LB;
     static constexpr int o_ub = o_rb + MAXROWS + 2;
     static constexpr int o_red = o_ub + 8;
-    static constexpr int o_int = o_red + 64;
+    static constexpr int o_int = o_red + 16;
     static constexpr int n_int = 2 * SMAX + 2 * HZ + HZ + 2 * HZ + 2 * SMAX + 16;
     static constexpr int o_bar = ((o_int + (n_int + 1) / 2 + 1) + 1) & ~1;  // mbarriers, 16-byte aligned
-    static constexpr int o_rows = o_bar + 4;           // 7 row arrays (s, lam, d, rp, wc, w, 1/s), sized at run time
+    // work region: three n-vectors + 6 row arrays (s, lam, lam/s, rp|ds, wc|dlam, w; run-time sized).
+    // The assembly phase, which runs before any of them is live, uses the same region for the
+    // per-stage dynamics pieces (a_*); the polish reuses the four dead row arrays (Nn, tvp).
+    static constexpr int o_work = o_bar + 4;
+    static constexpr int o_du = o_work;                // step / polish: particular solution
+    static constexpr int o_x = o_du + NV;              // H u + g, residual, right-hand side, solution
+    static constexpr int o_up = o_x + NV;              // polished point
+    static constexpr int o_rows = o_up + NV;
+    static constexpr int a_xref = o_work;
+    static constexpr int a_rinv = a_xref + HZ * 12;
+    static constexpr int a_psum = a_rinv + HZ * 9;
+    static constexpr int a_iwinv = a_psum + HZ * 9;
+    static constexpr int a_err = a_iwinv + HZ * 9;
+    static constexpr int a_footv = a_err + HZ * 12;
+    static constexpr int a_rot = a_footv + 24;
+    static constexpr int a_W = a_rot + 12;
+    static constexpr int a_Wp = a_W + SMAX * 3 * LB;
+    static constexpr int a_Vp = a_Wp + SMAX * 3;
+    static constexpr int a_end = a_Vp + SMAX * 3;
     // rows per array for `mb` inequality rows per block (even, so every array stays 16-byte aligned)
     __host__ __device__ static constexpr int row_stride(int mb) { return (mb * SMAX + 1) & ~1; }
+    __host__ __device__ static constexpr int imax(int a, int b) { return a > b ? a : b; }
     __host__ __device__ static constexpr int rows_doubles(int mb) {
-        return 7 * row_stride(mb) > PAIRS ? 7 * row_stride(mb) : PAIRS;
+        return imax(imax(6 * row_stride(mb), 2 * row_stride(mb) + SMAX * LB * LB + NV), a_end - o_rows);
     }
     __host__ __device__ static constexpr size_t bytes(int mb) { return size_t(o_rows + rows_doubles(mb)) * 8; }
+    // ---- per-group global scratch (L2 resident): H, the stage-pair kernels, and what only the output
+    //      stage needs again (saved after assembly, read back once) ----
+    static constexpr int g_H = 0;
+    static constexpr int g_pairs = g_H + MB;           // stage-pair kernels T (9) + cpp (1)
+    static constexpr int g_save = g_pairs + NPAIR * 10;  // copy of the a_* region
+    static constexpr int g_total = (g_save + (a_end - o_work) + 1) & ~1;
 };
 
 // ------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------
-template <int HZ, int SMAX, int LB, int NT>
-__global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
+// NW > 1 (walking class, NT == 32): NW independent robots per CTA, one warp each, kept in loose
+// lockstep by one mbarrier arrival per iteration so that the warps of an SM run the same code at
+// about the same time and share instruction-cache lines (the kernel is instruction-fetch bound
+// otherwise: profiles/r1_summary.md).
+template <int HZ, int SMAX, int LB, int NT, int NW>
+__global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
                                                        const int* __restrict__ work_list,
                                                        const int* __restrict__ work_count,
                                                        double* __restrict__ hscratch) {
     using L = TickLayout<HZ, SMAX, LB>;
     constexpr int E = LB * LB, TS = L::TS, NAB = L::NAB;
     constexpr int NPT = (LB * SMAX + NT - 1) / NT;  // variables per thread
-    extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x;
+    static_assert(NW == 1 || NT == 32, "several robots per CTA only with one warp per robot");
+    extern __shared__ __align__(16) double sm_cta[];
+    const int tid = threadIdx.x & (NT - 1);
+    const int wid = threadIdx.x / NT;                                   // robot slot inside the CTA
+    const int group = blockIdx.x * NW + wid, ngroups = gridDim.x * NW;  // persistent group id / count
+    const int per_group = (int)(L::bytes(p.mb) / 8);
+    double* sm = sm_cta + (size_t)wid * per_group;
+    uint64_t* lockbar = reinterpret_cast<uint64_t*>(sm_cta + (size_t)NW * per_group);  // CTA-wide lockstep barrier
 
     double* Mb = sm + L::o_M;
     double* s_in = sm + L::o_in;
-    double* cur = sm + L::o_cur;
     double* gv = sm + L::o_g;
     double* uv = sm + L::o_u;
     double* duv = sm + L::o_du;
     double* xv = sm + L::o_x;
-    double* tv = sm + L::o_t;
-    double* hd = sm + L::o_hd;
     double* upv = sm + L::o_up;
-    double* ppv = sm + L::o_pp;
+    double* ppv = duv;               // polish: particular solution (the step vector is dead then)
     const int mrs = L::row_stride(p.mb);
     double* r_s = sm + L::o_rows;
     double* r_l = r_s + mrs;
@@ -424,19 +437,8 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
     double* r_p = r_d + mrs;
     double* r_c = r_p + mrs;
     double* r_w = r_c + mrs;
-    double* r_is = r_w + mrs;
-    double* pairs = sm + L::o_rows;  // alias, assembly only
-    double* Nn = sm + L::o_N;
-    double* xref = sm + L::o_xref;
-    double* rinv = sm + L::o_rinv;
-    double* psum = sm + L::o_psum;
-    double* iwinv = sm + L::o_iwinv;
-    double* err = sm + L::o_err;
-    double* footv = sm + L::o_footv;
-    double* rotn = sm + L::o_rot;
-    double* Wm = sm + L::o_W;
-    double* Wp = sm + L::o_Wp;
-    double* Vp = sm + L::o_Vp;
+    double* Nn = r_d;                // polish: null-space blocks and one n-vector over the dead row arrays
+    double* tvp = Nn + SMAX * E;
     double* Cb = sm + L::o_Cb;
     double* rb = sm + L::o_rb;
     double* ub = sm + L::o_ub;
@@ -452,8 +454,39 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::o_bar);  // [0],[1] inputs, [2] H reload
 
     const int count = *work_count;
-    if ((int)blockIdx.x >= count) return;
-    double* hglob = hscratch + (size_t)blockIdx.x * L::MB;
+    uint32_t lockpar = 0u;
+    // loose lockstep: every warp arrives once per "step" (instance start, each iteration, each polish
+    // round, output); a warp that runs out of work drops out of the barrier for good
+    auto lock_sync = [&]() {
+        if constexpr (NW > 1) {
+            __syncwarp();
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(lockbar)) : "memory");
+            mbar_wait(lockbar, lockpar);
+            lockpar ^= 1u;
+        }
+    };
+    auto lock_drop = [&]() {
+        if constexpr (NW > 1) {
+            __syncwarp();
+            if (tid == 0) asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" ::"r"(smem_u32(lockbar)) : "memory");
+        }
+    };
+    // per-group scratch in global memory: plain (coherent) loads/stores, ordered by the group barrier
+    double* gbase = hscratch + (size_t)group * L::g_total;
+    double* hglob = gbase + L::g_H;
+    double* pairs = gbase + L::g_pairs;
+    double* gsave = gbase + L::g_save;
+    // assembly-phase arrays, aliased onto the work region
+    double* xref = sm + L::a_xref;
+    double* rinv = sm + L::a_rinv;
+    double* psum = sm + L::a_psum;
+    double* iwinv = sm + L::a_iwinv;
+    double* err = sm + L::a_err;
+    double* footv = sm + L::a_footv;
+    double* rotn = sm + L::a_rot;
+    double* Wm = sm + L::a_W;
+    double* Wp = sm + L::a_Wp;
+    double* Vp = sm + L::a_Vp;
 
     const int mb = p.mb;
     const double dt = p.dt;
@@ -474,21 +507,27 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], 1);
+        if (NW > 1 && wid == 0) mbar_init(lockbar, NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (io.use_tma && tid == 0) issue_loads(work_list[blockIdx.x], 0);
+    if (group >= count) {
+        lock_drop();
+        return;
+    }
+    if (io.use_tma && tid == 0) issue_loads(work_list[group], 0);
     uint32_t parity[2] = {0u, 0u};
     uint32_t hparity = 0u;
     int buf = 0;
 
-    for (int w = blockIdx.x; w < count; w += gridDim.x, buf ^= 1) {
+    for (int w = group; w < count; w += ngroups, buf ^= 1) {
         const int inst = work_list[w];
+        lock_sync();
         // ---- 0. inputs ---------------------------------------------------------------
+        double* cur = s_in + buf * IN_DOUBLES;
         if (io.use_tma) {
             mbar_wait(&bars[buf], parity[buf]);
             parity[buf] ^= 1u;
-            for (int i = tid; i < IN_DOUBLES; i += NT) cur[i] = s_in[buf * IN_DOUBLES + i];
         } else {
             for (int i = tid; i < 44; i += NT) {
                 double v = 0.0;
@@ -504,7 +543,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
         }
         for (int i = tid; i < 2 * HZ; i += NT) cont[i] = io.contact[(size_t)inst * 2 * HZ + i] ? 1 : 0;
         gsync<NT>();
-        if (io.use_tma && tid == 0 && w + (int)gridDim.x < count) issue_loads(work_list[w + gridDim.x], buf ^ 1);
+        if (io.use_tma && tid == 0 && w + ngroups < count) issue_loads(work_list[w + ngroups], buf ^ 1);
 
         const double* x_fb = cur;
         const double* foot = cur + 12;
@@ -805,8 +844,6 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     for (int a = 0; a < LB; ++a)
 #pragma unroll
                         for (int b = 0; b < a; ++b) blk[b * LB + a] = blk[a * LB + b];
-#pragma unroll
-                    for (int a = 0; a < LB; ++a) hd[jr * LB + a] = blk[a * LB + a];
                 }
                 tile_store<LB>(Mb + t * TS, blk);
             }
@@ -842,6 +879,8 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
             }
         }
         gsync<NT>();
+        // the assembly arrays are needed again only by the output stage: park them in the scratch
+        for (int i = tid; i < L::a_end - L::o_work; i += NT) gsave[i] = sm[L::o_work + i];
         // H -> global scratch (16-byte coalesced stores); TMA brings it back once per iteration
         {
             const int nd2 = (S * (S + 1) / 2) * TS / 2;
@@ -850,6 +889,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
             for (int i = tid; i < nd2; i += NT) dst[i] = src[i];
             asm volatile("fence.proxy.async;" ::: "memory");
         }
+        gsync<NT>();  // the work region changes hands: assembly arrays -> solver vectors / row arrays
         const uint32_t hbytes = (uint32_t)((S * (S + 1) / 2) * TS * 8);
         if (io.dbg_H != nullptr && w == 0) {
             const int nmax = 12 * HZ;
@@ -925,7 +965,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
             double gpart = 0.0;
             for (int i = tid; i < n; i += NT) gpart = fmax(gpart, fabs(gv[i]));
             const double gs = 1.0 + gmax<NT>(gpart, red);
-            const double mu0 = gsum<NT>(part, red) / (double)m;
+            const double mu0 = p.mu0_scale * gsum<NT>(part, red) / (double)m;
             BMPC_FOR_ROWS(r, j, k) r_l[r] = mu0 / r_s[r];
             gsync<NT>();
 
@@ -938,14 +978,13 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                         break;
                     }
                     ++it;
+                    lock_sync();
                     h_need();
-                    tile_symv<LB, NT>(Mb, S, uv, gv, tv);  // tv = Hc u + g
+                    tile_symv<LB, NT>(Mb, S, uv, gv, xv);  // xv = Hc u + g
                     part = 0.0;
                     BMPC_FOR_ROWS(r, j, k) {
                         const double s = r_s[r], l = r_l[r];
-                        const double is = 1.0 / s;
-                        r_is[r] = is;
-                        r_d[r] = l * is;
+                        r_d[r] = l / s;
                         r_p[r] = cdot(j, k, uv) + s - rb[k];
                         part += s * l;
                     }
@@ -953,8 +992,8 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     double rdp = 0.0;
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) {
-                        const double v = tv[i] + col_gather(i, r_l);
-                        tv[i] = v;  // stationarity residual rd
+                        const double v = xv[i] + col_gather(i, r_l);
+                        xv[i] = v;  // stationarity residual rd
                         rdp = fmax(rdp, fabs(v));
                     }
                     mu = gsum<NT>(part, red) / (double)m;
@@ -980,7 +1019,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     }
                     gsync<NT>();
 #pragma unroll 1
-                    for (int i = tid; i < n; i += NT) xv[i] = -tv[i] - col_gather(i, r_w);
+                    for (int i = tid; i < n; i += NT) xv[i] = -xv[i] - col_gather(i, r_w);
                     h_valid = false;
                     gsync<NT>();
                     if (!tile_factor<LB, NT>(Mb, S)) {
@@ -1008,7 +1047,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     sigma = sigma * sigma * sigma;
                     const double tgt = sigma * mu;
                     // corrector: du = du_aff + inv(M) C' wc,  wc = (dsa dla - sigma mu) / s
-                    BMPC_FOR_ROWS(r, j, k) r_c[r] = (r_c[r] - tgt) * r_is[r];
+                    BMPC_FOR_ROWS(r, j, k) r_c[r] = (r_c[r] - tgt) / r_s[r];
                     gsync<NT>();
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_c);
@@ -1041,7 +1080,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                             const double v = (r_s[r] + at * r_p[r]) * (r_l[r] + at * r_c[r]);
                             double vt = fmin(fmax(v, 0.1 * tgt), 10.0 * tgt) - v;
                             vt = fmax(vt, -10.0 * tgt);
-                            r_w[r] = -vt * r_is[r];
+                            r_w[r] = -vt / r_s[r];
                         }
                         gsync<NT>();
 #pragma unroll 1
@@ -1054,19 +1093,21 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                             const double ds = r_p[r] - cx;
                             const double dl = r_c[r] + r_d[r] * cx - r_w[r];
                             ratio = fmaxf(ratio, fmaxf(step_ratio(ds, r_s[r]), step_ratio(dl, r_l[r])));
-                            r_w[r] = ds;   // candidate direction (own row only)
-                            r_is[r] = dl;
                         }
                         ratio = gmaxf<NT>(ratio, red);
                         const double a3 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
                         if (isfinite(ratio) && a3 > a2) {
                             a2 = a3;
+                            BMPC_FOR_ROWS(r, j, k) {
+                                const double cx = cdot(j, k, xv);
+                                r_p[r] -= cx;
+                                r_c[r] += r_d[r] * cx - r_w[r];
+                            }
 #pragma unroll 1
                             for (int i = tid; i < n; i += NT) duv[i] += xv[i];
-                            BMPC_FOR_ROWS(r, j, k) r_p[r] = r_w[r], r_c[r] = r_is[r];
                         }
                     }
-                    const double alpha = 0.995 * a2;
+                    const double alpha = (it > 14 ? 0.9 : p.step_frac) * a2;  // late iterations: stay well inside (anti-stall)
                     BMPC_FOR_ROWS(r, j, k) {
                         r_s[r] += alpha * r_p[r];
                         r_l[r] += alpha * r_c[r];
@@ -1079,18 +1120,20 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                 // ============================ active-set polish ============================
                 // guess: row active when its barrier weight lam/s dominates the curvature along it
                 for (int j = tid; j < S; j += NT) amask[j] = 0;
+                h_need();  // diag(Hc) is read from the tile matrix
                 gsync<NT>();
                 BMPC_FOR_ROWS(r, j, k) {
                     const double* cb = Cb + k * LB;
-                    const double* hh = hd + j * LB;
+                    const double* hh = Mb + tidx(j, j) * TS;
                     double th = 0.0, aa = 0.0;
 #pragma unroll
-                    for (int c = 0; c < LB; ++c) th += cb[c] * cb[c] * hh[c], aa += cb[c] * cb[c];
+                    for (int c = 0; c < LB; ++c) th += cb[c] * cb[c] * hh[c * (LB + 1)], aa += cb[c] * cb[c];
                     if (r_l[r] * fmax(aa * aa, 1e-300) > th * r_s[r]) atomicOr(&amask[j], 1 << k);
                 }
                 gsync<NT>();
                 bool ok = false;
                 for (int round = 0; round < 4; ++round) {
+                    lock_sync();
                     // per block: affine set of the active rows  u_b = p_b + N_b w_b
                     int bad_blk = 0;
                     for (int j = tid; j < S; j += NT) {
@@ -1101,14 +1144,14 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     if (gany<NT>(bad_blk)) break;
                     gsync<NT>();
                     h_need();
-                    tile_symv<LB, NT>(Mb, S, ppv, gv, tv);  // tv = Hc p + g
+                    tile_symv<LB, NT>(Mb, S, ppv, gv, tvp);  // Hc p + g
                     gsync<NT>();
                     // reduced system, padded to the tile grid: tile <- N_jr' H N_jc (+ I on the padding)
                     for (int i = tid; i < n; i += NT) {
                         const int j = i / LB, a = i - j * LB;
                         double acc = 0.0;
 #pragma unroll
-                        for (int c = 0; c < LB; ++c) acc += Nn[j * E + c * LB + a] * tv[j * LB + c];
+                        for (int c = 0; c < LB; ++c) acc += Nn[j * E + c * LB + a] * tvp[j * LB + c];
                         xv[i] = (a < bdim[j]) ? -acc : 0.0;
                     }
                     {
@@ -1177,13 +1220,13 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
                     }
                     // dual check: minus the gradient must be a non-negative combination of the active rows
                     h_need();
-                    tile_symv<LB, NT>(Mb, S, upv, gv, tv);
+                    tile_symv<LB, NT>(Mb, S, upv, gv, tvp);
                     gsync<NT>();
                     int fail = 0;
                     for (int j = tid; j < S; j += NT) {
                         double rneg[LB];
 #pragma unroll
-                        for (int c = 0; c < LB; ++c) rneg[c] = -tv[j * LB + c];
+                        for (int c = 0; c < LB; ++c) rneg[c] = -tvp[j * LB + c];
                         unsigned drop = 0u;
                         if (block_dual_fast<LB>(Cb, mb, (unsigned)amask[j], r_l + j * mb, rneg, gs)) continue;
                         if (!block_dual_check<LB>(Cb, mb, (unsigned)amask[j], rneg, gs, &drop)) {
@@ -1219,6 +1262,10 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
         gsync<NT>();
 
         // ---- 6. outputs ----------------------------------------------------------------------
+        lock_sync();
+        // bring the assembly arrays back into the (now free) work region
+        for (int i = tid; i < L::a_end - L::o_work; i += NT) sm[L::o_work + i] = gsave[i];
+        gsync<NT>();
         // controls (h,12): swing feet 0, pinned components at their bound (MPC.py:300-302)
         double umax_part = 0.0;
         for (int e = tid; e < HZ * 12; e += NT) {
@@ -1234,7 +1281,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
             }
             io.controls[(size_t)inst * HZ * 12 + e] = val;
             umax_part = fmax(umax_part, fabs(val));
-            if (s == 0) xv[c12] = val;  // first-stage input for the torque map (xv is free now)
+            if (s == 0) gv[c12] = val;  // first-stage input for the torque map (the gradient is dead now)
         }
         const double uscale = fmax(1.0, gmax<NT>(umax_part, red));
         // predicted states (h,13): X_i = free response + sum_j dX_i/du_j u_j
@@ -1297,7 +1344,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
         if (io.do_lowlevel && io.tau && tid < 2) {
             const int leg = tid;
             double tl[5];
-            lowlevel_leg(p, x_fb, io.t_swing[inst], cur + 38, cur + 18, cur + 28, rotn, leg, (double)cont[leg], xv, tl);
+            lowlevel_leg(p, x_fb, io.t_swing[inst], cur + 38, cur + 18, cur + 28, rotn, leg, (double)cont[leg], gv, tl);
 #pragma unroll
             for (int c = 0; c < 5; ++c) io.tau[(size_t)inst * 10 + 5 * leg + c] = tl[c];
         }
@@ -1308,6 +1355,7 @@ __global__ void __launch_bounds__(NT) mpc_tick2_kernel(const __grid_constant__ D
         }
         gsync<NT>();
     }
+    lock_drop();
 }
 
 }  // namespace bmpc
