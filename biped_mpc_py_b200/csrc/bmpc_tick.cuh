@@ -106,23 +106,21 @@ __device__ __forceinline__ void tile_store(double* __restrict__ p, const double 
     if constexpr ((LB * LB) & 1) p[LB * LB - 1] = t[LB * LB - 1];
 }
 
-// Cholesky of a symmetric LB x LB tile (lower part used) and the inverse of the factor.
+// Cholesky of a symmetric LB x LB tile (lower part used).  Returns the factor in l (lower part)
+// with the RECIPROCALS of its diagonal on the diagonal (that is what every consumer needs).
 // Every lane of the group runs this on the same data (a broadcast read), so the result is in
 // registers everywhere and needs no exchange.  false on a non-positive pivot.
 template <int LB>
-__device__ __forceinline__ bool tile_chol_inv(const double (&a)[LB * LB], double (&li)[LB * LB]) {
-    double l[LB * LB];
-    double id[LB];
+__device__ __forceinline__ bool tile_chol(const double (&a)[LB * LB], double (&l)[LB * LB]) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < LB; ++j) {
         double djj = a[j * LB + j];
 #pragma unroll
         for (int k = 0; k < j; ++k) djj -= l[j * LB + k] * l[j * LB + k];
-        ok = ok && (djj > 0.0) && isfinite(djj);
+        ok = ok && (djj > 0.0) && (djj < 1e300);
         const double r = rsqrt(djj);
-        id[j] = r;
-        l[j * LB + j] = djj * r;
+        l[j * LB + j] = r;
 #pragma unroll
         for (int i = j + 1; i < LB; ++i) {
             double v = a[i * LB + j];
@@ -130,62 +128,48 @@ __device__ __forceinline__ bool tile_chol_inv(const double (&a)[LB * LB], double
             for (int k = 0; k < j; ++k) v -= l[i * LB + k] * l[j * LB + k];
             l[i * LB + j] = v * r;
         }
-    }
-    // inverse of the lower-triangular factor, column by column
 #pragma unroll
-    for (int c = 0; c < LB; ++c) {
-#pragma unroll
-        for (int i = 0; i < LB; ++i) {
-            if (i < c) {
-                li[i * LB + c] = 0.0;
-            } else if (i == c) {
-                li[i * LB + c] = id[c];
-            } else {
-                double v = 0.0;
-#pragma unroll
-                for (int k = c; k < i; ++k) v -= l[i * LB + k] * li[k * LB + c];
-                li[i * LB + c] = v * id[i];
-            }
-        }
+        for (int i = 0; i < j; ++i) l[i * LB + j] = 0.0;
     }
     return ok;
 }
 
-// In-place block Cholesky of the tile matrix in Mb (S block rows).  On return tile (jr,jc),
-// jr > jc, holds L(jr,jc) and the diagonal tile (j,j) holds inv(L(j,j)) (the solves only ever
-// need the inverse).  Uniform return value.
+// In-place block Cholesky of the tile matrix in Mb (S block rows), left in the SOLVE form
+// M = Lh D Lh' with Lh unit block-lower: tile (jr,jc), jr > jc, holds Lh(jr,jc) = L(jr,jc) inv(L(jc,jc))
+// and the diagonal tile (j,j) holds the Cholesky factor of D_j with reciprocal diagonal.
+// Uniform return value.
 template <int LB, int NT>
 __device__ __noinline__ bool tile_factor(double* __restrict__ Mb, int S) {
     constexpr int E = LB * LB, TS = TileT<LB>::TS;
     const int tid = threadIdx.x & (NT - 1);
     bool ok = true;
     for (int jc = 0; jc < S; ++jc) {
-        double li[E];
+        double l[E];
         {
             double dg[E];
             tile_load<LB>(Mb + tidx(jc, jc) * TS, dg);
-            ok = tile_chol_inv<LB>(dg, li) && ok;
+            ok = tile_chol<LB>(dg, l) && ok;
         }
         gsync<NT>();  // everyone has read the diagonal tile before it is overwritten
         if (!ok) return false;  // uniform: every lane factored the same tile
         const int below = S - 1 - jc;
-        // panel: L(jr,jc) = A(jr,jc) * inv(L(jc,jc))'
+        // panel: L(jr,jc) = A(jr,jc) inv(L(jc,jc))'  (forward substitution along each row)
         for (int t = tid; t < below; t += NT) {
             double* tp = Mb + tidx(jc + 1 + t, jc) * TS;
-            double a[E], o[E];
+            double a[E];
             tile_load<LB>(tp, a);
 #pragma unroll
-            for (int r = 0; r < LB; ++r)
+            for (int c = 0; c < LB; ++c)
 #pragma unroll
-                for (int c = 0; c < LB; ++c) {
-                    double v = 0.0;
+                for (int r = 0; r < LB; ++r) {
+                    double v = a[r * LB + c];
 #pragma unroll
-                    for (int k = 0; k <= c; ++k) v += a[r * LB + k] * li[c * LB + k];
-                    o[r * LB + c] = v;
+                    for (int k = 0; k < c; ++k) v -= a[r * LB + k] * l[c * LB + k];
+                    a[r * LB + c] = v * l[c * LB + c];
                 }
-            tile_store<LB>(tp, o);
+            tile_store<LB>(tp, a);
         }
-        if (tid == NT - 1) tile_store<LB>(Mb + tidx(jc, jc) * TS, li);
+        if (tid == NT - 1) tile_store<LB>(Mb + tidx(jc, jc) * TS, l);
         gsync<NT>();
         // trailing update: A(jr,jc2) -= L(jr,jc) L(jc2,jc)'   for jc < jc2 <= jr
         const int ntr = below * (below + 1) / 2;
@@ -196,22 +180,26 @@ __device__ __noinline__ bool tile_factor(double* __restrict__ Mb, int S) {
             const int c = t - r * (r + 1) / 2;
             const int jr = jc + 1 + r, jc2 = jc + 1 + c;
             double* tp = Mb + tidx(jr, jc2) * TS;
-            double acc[E], a[E], b[E];
+            double acc[E];
             tile_load<LB>(tp, acc);
-            tile_load<LB>(Mb + tidx(jr, jc) * TS, a);
-            tile_load<LB>(Mb + tidx(jc2, jc) * TS, b);
+            const double* ap = Mb + tidx(jr, jc) * TS;
+            const double* bp = Mb + tidx(jc2, jc) * TS;
+            // rolled over k: the body stays resident in the instruction cache (the kernel is fetch-bound)
+#pragma unroll 1
+            for (int k = 0; k < LB; ++k) {
+                double a[LB], b[LB];
 #pragma unroll
-            for (int k = 0; k < LB; ++k)
+                for (int x = 0; x < LB; ++x) a[x] = ap[x * LB + k], b[x] = bp[x * LB + k];
 #pragma unroll
                 for (int x = 0; x < LB; ++x)
 #pragma unroll
-                    for (int y = 0; y < LB; ++y) acc[x * LB + y] -= a[x * LB + k] * b[y * LB + k];
+                    for (int y = 0; y < LB; ++y) acc[x * LB + y] -= a[x] * b[y];
+            }
             tile_store<LB>(tp, acc);
         }
         gsync<NT>();
     }
-    // Solve form: M = Lh D Lh' with Lh unit block-lower, so every substitution step is ONE phase.
-    // Lh(jr,jc) = L(jr,jc) inv(L(jc,jc));  the diagonal tile becomes inv(D_j) = inv(L_jj)' inv(L_jj).
+    // solve form: Lh(jr,jc) = L(jr,jc) inv(L(jc,jc))  (backward substitution along each row)
     const int nlow = S * (S - 1) / 2;
     for (int t = tid; t < nlow; t += NT) {
         int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
@@ -219,41 +207,25 @@ __device__ __noinline__ bool tile_factor(double* __restrict__ Mb, int S) {
         if ((r + 1) * (r + 2) / 2 <= t) ++r;
         const int jc = t - r * (r + 1) / 2, jr = r + 1;  // strictly lower tiles
         double* tp = Mb + tidx(jr, jc) * TS;
-        double a[E], li[E], o[E];
+        double a[E], l[E];
         tile_load<LB>(tp, a);
-        tile_load<LB>(Mb + tidx(jc, jc) * TS, li);
+        tile_load<LB>(Mb + tidx(jc, jc) * TS, l);
 #pragma unroll
-        for (int x = 0; x < LB; ++x)
+        for (int c = LB - 1; c >= 0; --c)
 #pragma unroll
-            for (int y = 0; y < LB; ++y) {
-                double v = 0.0;
+            for (int x = 0; x < LB; ++x) {
+                double v = a[x * LB + c];
 #pragma unroll
-                for (int k = y; k < LB; ++k) v += a[x * LB + k] * li[k * LB + y];
-                o[x * LB + y] = v;
+                for (int k = c + 1; k < LB; ++k) v -= a[x * LB + k] * l[k * LB + c];
+                a[x * LB + c] = v * l[c * LB + c];
             }
-        tile_store<LB>(tp, o);
-    }
-    gsync<NT>();
-    for (int j = tid; j < S; j += NT) {
-        double* tp = Mb + tidx(j, j) * TS;
-        double li[E], o[E];
-        tile_load<LB>(tp, li);
-#pragma unroll
-        for (int x = 0; x < LB; ++x)
-#pragma unroll
-            for (int y = 0; y < LB; ++y) {
-                double v = 0.0;
-#pragma unroll
-                for (int k = (x > y ? x : y); k < LB; ++k) v += li[k * LB + x] * li[k * LB + y];
-                o[x * LB + y] = v;
-            }
-        tile_store<LB>(tp, o);
+        tile_store<LB>(tp, a);
     }
     gsync<NT>();
     return ok;
 }
 
-// x <- inv(M) x with the factor of tile_factor (unit block-lower Lh below the diagonal, inv(D_j)
+// x <- inv(M) x with the factor of tile_factor (unit block-lower Lh below the diagonal, chol(D_j)
 // on it).  x has LB*S entries in shared memory.  One group barrier per block step.
 template <int LB, int NT, int NPT>
 __device__ __noinline__ void tile_solve(const double* __restrict__ Mb, int S, double* __restrict__ x) {
@@ -275,27 +247,29 @@ __device__ __noinline__ void tile_solve(const double* __restrict__ Mb, int S, do
         }
         gsync<NT>();
     }
-    // middle: w_j = inv(D_j) z_j
-    {
-        double w[NPT];
+    // middle: w_j = inv(D_j) z_j by the two triangular substitutions with chol(D_j); one lane per
+    // block, which reads and writes only its own LB entries (no hazard, one barrier)
+    for (int j = tid; j < S; j += NT) {
+        double l[LB * LB], z[LB];
+        tile_load<LB>(Mb + tidx(j, j) * TS, l);
 #pragma unroll
-        for (int q = 0; q < NPT; ++q) {
-            const int i = tid + q * NT;
-            w[q] = 0.0;
-            if (i < n) {
-                const int j = i / LB, a = i - j * LB;
-                const double* di = Mb + tidx(j, j) * TS + a * LB;
-                const double* zj = x + j * LB;
+        for (int a = 0; a < LB; ++a) z[a] = x[j * LB + a];
 #pragma unroll
-                for (int b = 0; b < LB; ++b) w[q] += di[b] * zj[b];
-            }
+        for (int a = 0; a < LB; ++a) {
+#pragma unroll
+            for (int b = 0; b < a; ++b) z[a] -= l[a * LB + b] * z[b];
+            z[a] *= l[a * LB + a];
         }
-        gsync<NT>();
 #pragma unroll
-        for (int q = 0; q < NPT; ++q)
-            if (tid + q * NT < n) x[tid + q * NT] = w[q];
-        gsync<NT>();
+        for (int a = LB - 1; a >= 0; --a) {
+#pragma unroll
+            for (int b = a + 1; b < LB; ++b) z[a] -= l[b * LB + a] * z[b];
+            z[a] *= l[a * LB + a];
+        }
+#pragma unroll
+        for (int a = 0; a < LB; ++a) x[j * LB + a] = z[a];
     }
+    gsync<NT>();
     // backward: x_r -= Lh(jc,r)' x_jc for r < jc
     for (int jc = S - 1; jc > 0; --jc) {
         const double* xc = x + jc * LB;
@@ -371,7 +345,8 @@ struct TickLayout {
     static constexpr int o_du = o_work;                // step / polish: particular solution
     static constexpr int o_x = o_du + NV;              // H u + g, residual, right-hand side, solution
     static constexpr int o_up = o_x + NV;              // polished point
-    static constexpr int o_rows = o_up + NV;
+    static constexpr int o_rd = o_up + NV;             // stationarity residual (carried by its recurrence)
+    static constexpr int o_rows = o_rd + NV;
     static constexpr int a_xref = o_work;
     static constexpr int a_rinv = a_xref + HZ * 12;
     static constexpr int a_psum = a_rinv + HZ * 9;
@@ -429,6 +404,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
     double* duv = sm + L::o_du;
     double* xv = sm + L::o_x;
     double* upv = sm + L::o_up;
+    double* rdv = sm + L::o_rd;
     double* ppv = duv;               // polish: particular solution (the step vector is dead then)
     const int mrs = L::row_stride(p.mb);
     double* r_s = sm + L::o_rows;
@@ -960,7 +936,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
         }
         int status = 1, it = 0;
         double mu = 0.0, rdmax = 0.0;
-        bool polished = false;
+        bool polished = false, rd_fresh = false;
         if (n > 0) {
             double gpart = 0.0;
             for (int i = tid; i < n; i += NT) gpart = fmax(gpart, fabs(gv[i]));
@@ -980,7 +956,6 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     ++it;
                     lock_sync();
                     h_need();
-                    tile_symv<LB, NT>(Mb, S, uv, gv, xv);  // xv = Hc u + g
                     part = 0.0;
                     BMPC_FOR_ROWS(r, j, k) {
                         const double s = r_s[r], l = r_l[r];
@@ -989,15 +964,22 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         part += s * l;
                     }
                     gsync<NT>();
-                    double rdp = 0.0;
+                    if (!rd_fresh) {
+                        // stationarity residual rd = Hc u + g + C' lam, evaluated once; a Newton step of
+                        // length alpha scales it by (1 - alpha) exactly, so afterwards it is carried by
+                        // that recurrence (the polish re-derives everything exactly anyway)
+                        tile_symv<LB, NT>(Mb, S, uv, gv, rdv);
+                        double rdp = 0.0;
 #pragma unroll 1
-                    for (int i = tid; i < n; i += NT) {
-                        const double v = xv[i] + col_gather(i, r_l);
-                        xv[i] = v;  // stationarity residual rd
-                        rdp = fmax(rdp, fabs(v));
+                        for (int i = tid; i < n; i += NT) {
+                            const double v = rdv[i] + col_gather(i, r_l);
+                            rdv[i] = v;
+                            rdp = fmax(rdp, fabs(v));
+                        }
+                        rdmax = gmax<NT>(rdp, red);
+                        rd_fresh = true;
                     }
                     mu = gsum<NT>(part, red) / (double)m;
-                    rdmax = gmax<NT>(rdp, red);
                     if (mu <= mu_target && rdmax <= p.rd_tol * mu_target) {
                         status = 0;
                         break;
@@ -1019,7 +1001,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     }
                     gsync<NT>();
 #pragma unroll 1
-                    for (int i = tid; i < n; i += NT) xv[i] = -xv[i] - col_gather(i, r_w);
+                    for (int i = tid; i < n; i += NT) xv[i] = -rdv[i] - col_gather(i, r_w);
                     h_valid = false;
                     gsync<NT>();
                     if (!tile_factor<LB, NT>(Mb, S)) {
@@ -1113,7 +1095,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         r_l[r] += alpha * r_c[r];
                     }
 #pragma unroll 1
-                    for (int i = tid; i < n; i += NT) uv[i] += alpha * duv[i];
+                    for (int i = tid; i < n; i += NT) uv[i] += alpha * duv[i], rdv[i] *= (1.0 - alpha);
+                    rdmax *= (1.0 - alpha);
                     h_issue();  // (syncs) bring H back while the next iteration starts
                 }
 
