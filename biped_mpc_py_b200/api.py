@@ -163,6 +163,43 @@ class BatchedMPC:
                                                  self._check(out, (n, 6), f64, "out"), self._stream_ptr(stream)))
         return out
 
+    def rollout(self, x, foot, tick, gait, q, qd, ticks: int, warm_start: bool = True, n_log: int = 0, stream=None):
+        """Closed loop for N robots, ``ticks`` control ticks (``bmpc_rollout``; rules R1-R6 in DESIGN.md 9).
+
+        ``x`` (N,12), ``foot`` (N,6) and ``tick`` (N,) int32 are device tensors advanced IN PLACE;
+        ``gait`` (N,) uint8, ``q``/``qd`` (N,10) are held fixed.  Returns dict(stats=..., and with
+        ``n_log`` > 0 the device logs x_log (ticks+1,n_log,12), foot_log, u0_log (ticks,n_log,12), tau_log).
+        ``stats`` is a device int64[8] tensor (see include/biped_mpc_b200.h); read it after a sync.
+        """
+        torch = _torch()
+        n = int(x.shape[0])
+        if n > self.max_batch:
+            raise ValueError("batch larger than max_batch")
+        f64, dev = torch.float64, self.device
+        args = [self._check(x, (n, 12), f64, "x"), self._check(foot, (n, 6), f64, "foot"),
+                self._check(tick, (n,), torch.int32, "tick"), self._check(gait, (n,), torch.uint8, "gait"),
+                self._check(q, (n, 10), f64, "q"), self._check(qd, (n, 10), f64, "qd")]
+        out = dict(stats=torch.zeros(8, dtype=torch.int64, device=dev))
+        null = ctypes.c_void_p(0)
+        logs = [null] * 4
+        if n_log > 0:
+            out["x_log"] = torch.empty((ticks + 1, n_log, 12), dtype=f64, device=dev)
+            out["foot_log"] = torch.empty((ticks + 1, n_log, 6), dtype=f64, device=dev)
+            out["u0_log"] = torch.empty((ticks, n_log, 12), dtype=f64, device=dev)
+            out["tau_log"] = torch.empty((ticks, n_log, 10), dtype=f64, device=dev)
+            logs = [ctypes.c_void_p(out[k].data_ptr()) for k in ("x_log", "foot_log", "u0_log", "tau_log")]
+        _lib.check(self._lib.bmpc_rollout(self._h, n, int(ticks), *args, int(bool(warm_start)), int(n_log), *logs,
+                                          ctypes.c_void_p(out["stats"].data_ptr()), self._stream_ptr(stream)))
+        return out
+
+    @staticmethod
+    def rollout_stats(stats) -> Dict[str, float]:
+        """Name the entries of a rollout ``stats`` tensor (synchronises)."""
+        v = [int(a) for a in stats.cpu().tolist()]
+        rt = max(1, v[4])
+        return dict(robot_ticks=v[4], mean_iters=v[0] / rt, max_iters=v[3], not_optimal=v[1], bad_input=v[2],
+                    warm_hits=v[5], warm_hit_rate=v[5] / rt, falls=v[6])
+
     def debug_assemble(self, x_fb, phase_k, foot, contact):
         """Reduced condensed QP (Hc, g) of ONE instance as numpy arrays (parity tests)."""
         torch = _torch()

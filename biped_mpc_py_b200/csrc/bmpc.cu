@@ -12,6 +12,7 @@
 #include <string>
 
 #include "../../include/biped_mpc_b200.h"
+#include "bmpc_rollout.cuh"
 #include "bmpc_small.cuh"
 #include "bmpc_tick.cuh"
 
@@ -55,6 +56,17 @@ struct bmpc_handle {
     int* d_lists = nullptr;   // [2][max_batch]
     int* d_counts = nullptr;  // [2]
     int64_t launches = 0;
+    // closed-loop rollout workspace (allocated on the first bmpc_rollout call, max_batch sized)
+    struct {
+        uint8_t* contact = nullptr;
+        int32_t* phase_k = nullptr;
+        double* t_swing = nullptr;
+        double* controls = nullptr;
+        double* tau = nullptr;
+        int32_t* status = nullptr;
+        int32_t* iters = nullptr;
+        int32_t* ws_mask = nullptr;
+    } ro;
     int timing = 0;              // record CUDA events around each kernel of a tick
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -83,6 +95,7 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     d.gondzio = 1;
     d.init_fz_frac = 0.2;   // start point: 20 % of the fz range, friction/moment components centred
     d.mu0_scale = 0.1;      // initial complementarity = mu0_scale * mean slack
+    d.warm_rounds = 6;      // polish rounds allowed to a warm-started tick before it falls back to the cold path
     d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
     memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));
     memcpy(d.Q, P.Q, sizeof(d.Q));
@@ -220,11 +233,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
     const int nww = ew ? atoi(ew) : 5, nts = es ? atoi(es) : 128;  // walking: robots per CTA; standing: threads per robot
     if (h->dp.LB == 5) {
         rc = (nww == 1 ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
-              : nww == 2 ? setup_variant<10, 10, 5, 32, 2>(h->bucket[0], h->num_sms, h->dp.mb)
-              : nww == 3 ? setup_variant<10, 10, 5, 32, 3>(h->bucket[0], h->num_sms, h->dp.mb)
-              : nww == 4 ? setup_variant<10, 10, 5, 32, 4>(h->bucket[0], h->num_sms, h->dp.mb)
-              : nww == 5 ? setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)
-                         : setup_variant<10, 10, 5, 32, 10>(h->bucket[0], h->num_sms, h->dp.mb)) ||
+                         : setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)) ||
              (nts == 256 ? setup_variant<10, 20, 5, 256, 1>(h->bucket[1], h->num_sms, h->dp.mb)
                          : setup_variant<10, 20, 5, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb));
     } else {
@@ -252,6 +261,8 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaFree(h->d_lists);
     cudaFree(h->d_counts);
     for (int b = 0; b < 2; ++b) cudaFree(h->bucket[b].d_scratch);
+    cudaFree(h->ro.contact), cudaFree(h->ro.phase_k), cudaFree(h->ro.t_swing), cudaFree(h->ro.controls);
+    cudaFree(h->ro.tau), cudaFree(h->ro.status), cudaFree(h->ro.iters), cudaFree(h->ro.ws_mask);
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -318,6 +329,55 @@ int bmpc_foot_positions(bmpc_handle* h, int n, const double* x_fb, const double*
     foot_positions_kernel<<<(total + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         h->dp, n, x_fb, q, pf_w);
     h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bmpc_rollout(bmpc_handle* h, int n, int ticks, double* x, double* foot, int32_t* tick, const uint8_t* gait,
+                 const double* q, const double* qd, int warm_start, int n_log, double* x_log, double* foot_log,
+                 double* u0_log, double* tau_log, uint64_t* stats, void* stream) {
+    if (!h) return fail("bmpc_rollout: null handle");
+    if (!x || !foot || !tick || !gait || !q || !qd) return fail("bmpc_rollout: null required pointer");
+    if (n <= 0 || ticks <= 0) return 0;
+    if (n > h->max_batch) return fail("batch larger than max_batch given to bmpc_create");
+    if (n_log < 0 || n_log > n) return fail("bmpc_rollout: n_log must be in [0, n]");
+    if (n_log > 0 && (!x_log || !foot_log || !u0_log || !tau_log)) return fail("bmpc_rollout: n_log > 0 needs all four log buffers");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int hz = h->dp.h;
+    const size_t nb = (size_t)h->max_batch;
+    if (!h->ro.contact) {
+        CUDA_TRY(cudaMalloc(&h->ro.contact, nb * hz * 2));
+        CUDA_TRY(cudaMalloc(&h->ro.phase_k, nb * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&h->ro.t_swing, nb * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->ro.controls, nb * hz * 12 * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->ro.tau, nb * 10 * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->ro.status, nb * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&h->ro.iters, nb * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&h->ro.ws_mask, nb * hz * 2 * sizeof(int32_t)));
+    }
+    RolloutPtrs r;
+    memset(&r, 0, sizeof(r));
+    r.x = x, r.foot = foot, r.tick = tick, r.gait = gait, r.q = q;
+    r.contact = h->ro.contact, r.phase_k = h->ro.phase_k, r.t_swing = h->ro.t_swing;
+    r.controls = h->ro.controls, r.tau = h->ro.tau, r.status = h->ro.status, r.iters = h->ro.iters;
+    r.n_log = n_log, r.x_log = x_log, r.foot_log = foot_log, r.u0_log = u0_log, r.tau_log = tau_log;
+    r.stats = reinterpret_cast<unsigned long long*>(stats);
+    IoPtrs io;
+    memset(&io, 0, sizeof(io));
+    io.x_fb = x, io.phase_k = h->ro.phase_k, io.t_swing = h->ro.t_swing, io.foot = foot, io.contact = h->ro.contact;
+    io.q = q, io.qd = qd, io.pf_w = foot;  // R3: pf_w = foot
+    io.controls = h->ro.controls, io.tau = h->ro.tau, io.status = h->ro.status, io.iters = h->ro.iters;
+    io.do_lowlevel = 1;
+    io.ws_mask = warm_start ? h->ro.ws_mask : nullptr;
+    const int threads = 128, blocks = (n + threads - 1) / threads;
+    for (int k = 0; k < ticks; ++k) {
+        rollout_prepare_kernel<<<blocks, threads, 0, st>>>(h->dp, r, n, k);
+        io.warm = (warm_start && k > 0) ? 1 : 0;  // the first tick of a call is always cold
+        if (launch_tick(h, n, io, st)) return 1;
+        rollout_advance_kernel<<<blocks, threads, 0, st>>>(h->dp, r, n, k);
+        h->launches += 2;
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

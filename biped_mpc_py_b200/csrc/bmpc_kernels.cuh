@@ -17,7 +17,7 @@ constexpr int IN_DOUBLES = 48;  // x_fb 12 | foot 6 | q 10 | qd 10 | pf_w 6 | pa
 enum RowKind { ROW_LO = 0, ROW_HI = 1, ROW_FRIC = 2, ROW_LINE = 3 };
 
 struct DevParams {
-    int h, extend, LB, mb, npinned, max_iter, gondzio;
+    int h, extend, LB, mb, npinned, max_iter, gondzio, warm_rounds;
     int comps[6];
     int pinned[6];
     int row_kind[MAXROWS];
@@ -45,6 +45,8 @@ struct IoPtrs {
     double* dbg_H;           // debug: dense Hc [nmax*nmax] of work item 0, or null
     double* dbg_g;
     int32_t* dbg_n;
+    int32_t* ws_mask;        // [N,2h] warm-start store: certified active-row mask per (stage, foot), -1 = none; or null
+    int warm;                // use ws_mask as the starting active set (it is always written when non-null)
     int use_tma;             // inputs are 16-byte aligned: stage them with cp.async.bulk
     int do_lowlevel;         // q/qd/pf_w/t_swing valid, write tau
 };

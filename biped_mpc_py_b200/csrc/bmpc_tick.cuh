@@ -630,6 +630,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                 for (int i = tid; i < 10; i += NT) io.tau[(size_t)inst * 10 + i] = 0.0;
             if (io.fric_active)
                 for (int i = tid; i < HZ; i += NT) io.fric_active[(size_t)inst * HZ + i] = 0;
+            if (io.ws_mask)
+                for (int i = tid; i < 2 * HZ; i += NT) io.ws_mask[(size_t)inst * 2 * HZ + i] = -1;
             if (tid == 0) {
                 io.status[inst] = 3;
                 io.iters[inst] = 0;
@@ -942,13 +944,20 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
             for (int i = tid; i < n; i += NT) gpart = fmax(gpart, fabs(gv[i]));
             const double gs = 1.0 + gmax<NT>(gpart, red);
             const double mu0 = p.mu0_scale * gsum<NT>(part, red) / (double)m;
-            BMPC_FOR_ROWS(r, j, k) r_l[r] = mu0 / r_s[r];
             gsync<NT>();
 
             double mu_target = p.mu_tol * gs;
-            for (int attempt = 0; attempt < 3 && !polished; ++attempt, mu_target *= 1e-2) {
+            // attempt -1 (warm start, closed loop only): skip the interior point and polish from the
+            // previous tick's active set shifted by one stage; if that does not certify, the cold
+            // path below runs exactly as if no warm start had been given
+            const bool warm = io.ws_mask != nullptr && io.warm != 0;
+            for (int attempt = warm ? -1 : 0; attempt < 3 && !polished; mu_target *= (attempt >= 0 ? 1e-2 : 1.0), ++attempt) {
+                if (attempt == 0) {
+                    BMPC_FOR_ROWS(r, j, k) r_l[r] = mu0 / r_s[r];
+                    gsync<NT>();
+                }
                 // ======================= interior-point iterations =========================
-                while (true) {
+                while (attempt >= 0) {
                     if (it >= p.max_iter) {
                         status = 1;
                         break;
@@ -1101,6 +1110,20 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                 }
 
                 // ============================ active-set polish ============================
+                if (attempt < 0) {
+                    // guess: the certified active set of the previous tick, one stage later (same absolute
+                    // time); the new last stage copies the old last stage.  No multiplier estimate: lam = 0
+                    const int32_t* wm = io.ws_mask + (size_t)inst * 2 * HZ;
+                    for (int j = tid; j < S; j += NT) {
+                        const int s = blk_stage[j], l = blk_foot[j], s1 = min(s + 1, HZ - 1);
+                        int mk = wm[2 * s1 + l];
+                        if (mk < 0) mk = wm[2 * s1 + (1 - l)];
+                        if (mk < 0) mk = wm[2 * s + l];
+                        amask[j] = mk < 0 ? 0 : mk;
+                    }
+                    BMPC_FOR_ROWS(r, j, k) r_l[r] = 0.0;
+                    gsync<NT>();
+                } else {
                 // guess: row active when its barrier weight lam/s dominates the curvature along it
                 for (int j = tid; j < S; j += NT) amask[j] = 0;
                 h_need();  // diag(Hc) is read from the tile matrix
@@ -1114,8 +1137,10 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     if (r_l[r] * fmax(aa * aa, 1e-300) > th * r_s[r]) atomicOr(&amask[j], 1 << k);
                 }
                 gsync<NT>();
+                }
                 bool ok = false;
-                for (int round = 0; round < 4; ++round) {
+                const int max_rounds = attempt < 0 ? p.warm_rounds : 4;
+                for (int round = 0; round < max_rounds; ++round) {
                     lock_sync();
                     // per block: affine set of the active rows  u_b = p_b + N_b w_b
                     int bad_blk = 0;
@@ -1330,6 +1355,12 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
             lowlevel_leg(p, x_fb, io.t_swing[inst], cur + 38, cur + 18, cur + 28, rotn, leg, (double)cont[leg], gv, tl);
 #pragma unroll
             for (int c = 0; c < 5; ++c) io.tau[(size_t)inst * 10 + 5 * leg + c] = tl[c];
+        }
+        if (io.ws_mask) {  // certified active set per (stage, foot) slot for the next tick's warm start
+            for (int e = tid; e < 2 * HZ; e += NT) {
+                const int b = blockOf[e];
+                io.ws_mask[(size_t)inst * 2 * HZ + e] = (polished && b >= 0) ? amask[b] : -1;
+            }
         }
         if (tid == NT - 1) {
             io.status[inst] = status;

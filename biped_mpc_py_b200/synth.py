@@ -74,3 +74,34 @@ def make_batch(n: int, shard_index: int = 0, mpc=None, biped=None, walking_prob:
     contact, phase_k = batch_contact_and_phase(t, gait, mpc, extend=extend)
     return dict(x_fb=np.ascontiguousarray(x_fb), t=t, q=q, qd=qd, gait=gait, pf_w=pf_w, foot=pf_w.copy(),
                 contact=contact, phase_k=phase_k)
+
+
+def rollout_biped():
+    """Robot parameters of the closed-loop rollout: the reference's ``Biped`` (MPC.py:34-48) with a
+    symmetric horizontal force box ``f_min = [-f_max_x, -f_max_y, 0]``.
+
+    With the reference default ``f_min = 0`` (MPC.py:46) the box rows force fx, fy >= 0 (MPC.py:245-246),
+    so a robot can never brake a positive velocity: its closed loop drifts and diverges within ~150 ticks
+    even from the nominal standing state (measured with oracle/rollout.py).  The single-tick parity
+    targets all use the reference defaults; only the rollout workload uses this variant."""
+    b = Biped()
+    b.f_min = np.array([[-float(b.f_max[0, 0])], [-float(b.f_max[1, 0])], [0.0]])
+    return b
+
+
+def make_rollout_batch(n: int, shard_index: int = 0, biped=None, walking_prob: float = 0.85):
+    """Initial conditions of the closed-loop rollout (BASELINE.json configs[4]): the reference's nominal
+    state (MPC.py:13-16) plus a small perturbation - euler ~ U(-0.05,0.05) rad, x,y,z offsets ~ U(-0.02,0.02) m,
+    omega, v ~ N(0,0.05^2), q = nominal + N(0,0.02^2) - a random integer gait clock in [0,10) and
+    ``foot = getFootPositionWorld(x, q)``; walking with probability 0.85 else standing."""
+    biped = biped if biped is not None else rollout_biped()
+    rng = np.random.default_rng(SEED + 7919 + int(shard_index))
+    x = np.array([0, 0, 0, 0, 0, 0.53, 0, 0, 0, 0, 0, 0], dtype=np.float64)[None, :] + np.concatenate(
+        [rng.uniform(-0.05, 0.05, (n, 3)), rng.uniform(-0.02, 0.02, (n, 3)), rng.normal(0, 0.05, (n, 3)),
+         rng.normal(0, 0.05, (n, 3))], axis=1)
+    q = Q_NOMINAL[None, :] + rng.normal(0, 0.02, (n, 10))
+    qd = np.zeros((n, 10))
+    tick = rng.integers(0, 10, n).astype(np.int32)
+    gait = (rng.uniform(size=n) < walking_prob).astype(np.uint8)
+    foot = foot_positions_world(x, q, biped)
+    return dict(x=np.ascontiguousarray(x), foot=np.ascontiguousarray(foot), tick=tick, gait=gait, q=q, qd=qd)

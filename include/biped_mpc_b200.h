@@ -101,6 +101,28 @@ int bmpc_lowlevel(bmpc_handle* h, int n,
 /* getFootPositionWorld (MPC.py:406-424) for N robots: x_fb[N,12], q[N,10] -> pf_w[N,6]. */
 int bmpc_foot_positions(bmpc_handle* h, int n, const double* x_fb, const double* q, double* pf_w, void* stream);
 
+/* Closed-loop batched rollout (BASELINE.json configs[4]): `ticks` control ticks for N
+ * robots, each tick = bmpc_step + one step of the reference's own discretised single-rigid-body
+ * model x+ = A_0 [x;1] + B_0 u_0 (MPC.py:148-185, 206-208) + gait clock + touchdown foothold.
+ * The reference has no loop (MPC.py:475-495 runs one tick); the rules R1-R6 are stated in
+ * DESIGN.md section 9 and restated for the CPU in oracle/rollout.py.
+ *   in/out: x[N,12]  foot[N,6] (= pf_w)  tick[N] (int32 gait clock; phase = tick % 10, MPC.py:56-58)
+ *   in    : gait[N] uint8 (1 walking / 0 standing, MPC.py:18)  q[N,10]  qd[N,10] (held fixed)
+ *           warm_start != 0: after the first tick, each solve starts from the previous tick's
+ *           certified active set shifted by one stage and goes straight to the active-set
+ *           polish (falls back to the cold interior point when that does not certify; results are
+ *           the same certified optimum either way - the reference solves cold, MPC.py:297)
+ *   logs  : first n_log robots: x_log[ticks+1,n_log,12] foot_log[ticks+1,n_log,6]
+ *           u0_log[ticks,n_log,12] tau_log[ticks,n_log,10] (all nullable when n_log == 0)
+ *   stats : uint64[8] DEVICE, accumulated (caller zeroes): [0] sum of interior-point iterations
+ *           [1] ticks not certified optimal [2] bad-input ticks [3] max iterations [4] robot-ticks
+ *           [5] ticks solved by the warm polish alone (0 iterations) [6] falls (rule R7).  Nullable. */
+int bmpc_rollout(bmpc_handle* h, int n, int ticks,
+                 double* x, double* foot, int32_t* tick, const uint8_t* gait,
+                 const double* q, const double* qd, int warm_start,
+                 int n_log, double* x_log, double* foot_log, double* u0_log, double* tau_log,
+                 uint64_t* stats, void* stream);
+
 /* Debug / parity: the contact-reduced condensed QP of instance `index` of the last
  * bmpc_step/bmpc_solve inputs.  Hc_out[nmax*nmax] row-major (nmax = 12*h), g_out[nmax],
  * n_out = number of reduced variables, all DEVICE pointers.  Synchronous. */
