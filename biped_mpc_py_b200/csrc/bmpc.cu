@@ -78,7 +78,7 @@ namespace {
 // parameter values (dropping them does not change the feasible set).
 int build_dev_params(const bmpc_params& P, DevParams& d) {
     memset(&d, 0, sizeof(d));
-    if (P.h != 10) return fail("horizon must be 10 in this build (h=30 is not instantiated yet)");
+    if (P.h != 10 && P.h != 30) return fail("horizon must be 10 or 30 (the instantiated kernels)");
     d.h = P.h;
     d.extend = P.extend_gait;
     d.dt = P.dt;
@@ -159,10 +159,10 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     return 0;
 }
 
-template <int HZ, int SMAX, int LB, int NT, int NW>
+template <int HZ, int SMAX, int LB, int NT, int NW, bool MG = false>
 int setup_variant(Variant& v, int num_sms, int mb) {
-    using L = TickLayout<HZ, SMAX, LB>;
-    v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT, NW>;
+    using L = TickLayout<HZ, SMAX, LB, MG>;
+    v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT, NW, MG>;
     v.smem = L::bytes(mb) * NW + 16;  // + the CTA-wide lockstep mbarrier
     v.threads = NT * NW;
     v.per_cta = NW;
@@ -231,7 +231,16 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
     const char* ew = getenv("BMPC_NW_WALK");
     const char* es = getenv("BMPC_NT_STAND");
     const int nww = ew ? atoi(ew) : 5, nts = es ? atoi(es) : 128;  // walking: robots per CTA; standing: threads per robot
-    if (h->dp.LB == 5) {
+    if (h->dp.h == 30) {
+        // h = 30 (BASELINE.json configs[3]): walking class S <= 30 with the tile matrix in shared memory
+        // (97 KB, one CTA per SM), standing class S <= 60 with it in the L2-resident scratch (380 KB)
+        if (h->dp.LB != 5) {
+            delete h;
+            return fail("h = 30 is instantiated for the reference limit structure only (exactly one pinned component)");
+        }
+        rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
+             setup_variant<30, 60, 5, 256, 1, true>(h->bucket[1], h->num_sms, h->dp.mb);
+    } else if (h->dp.LB == 5) {
         rc = (nww == 1 ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
                          : setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)) ||
              (nts == 256 ? setup_variant<10, 20, 5, 256, 1>(h->bucket[1], h->num_sms, h->dp.mb)

@@ -317,7 +317,9 @@ __device__ __noinline__ void tile_symv(const double* __restrict__ Mb, int S, con
 // ------------------------------------------------------------------------------------
 // shared-memory layout (offsets in doubles)
 // ------------------------------------------------------------------------------------
-template <int HZ, int SMAX, int LB>
+// MG: the tile matrix does not fit in shared memory (h = 30 standing: 1,830 tiles, 380 KB) and lives in
+// the per-group global scratch next to H (L2 resident); everything else is unchanged.
+template <int HZ, int SMAX, int LB, bool MG = false>
 struct TickLayout {
     static constexpr int TS = TileT<LB>::TS;
     static constexpr int N = LB * SMAX;
@@ -328,7 +330,7 @@ struct TickLayout {
     static constexpr int NAB = LB * (LB + 1) / 2;
     // ---- shared memory ----
     static constexpr int o_M = 0;
-    static constexpr int o_in = o_M + MB;              // 2 x IN_DOUBLES TMA destinations (inputs, double buffered)
+    static constexpr int o_in = o_M + (MG ? 0 : MB);   // 2 x IN_DOUBLES TMA destinations (inputs, double buffered)
     static constexpr int o_g = o_in + 2 * IN_DOUBLES;
     static constexpr int o_u = o_g + NV;
     static constexpr int o_Cb = o_u + NV;
@@ -368,7 +370,8 @@ struct TickLayout {
     // ---- per-group global scratch (L2 resident): H, the stage-pair kernels, and what only the output
     //      stage needs again (saved after assembly, read back once) ----
     static constexpr int g_H = 0;
-    static constexpr int g_pairs = g_H + MB;           // stage-pair kernels T (9) + cpp (1)
+    static constexpr int g_M = g_H + MB;               // MG only: the working copy (H + barrier terms, then the factor)
+    static constexpr int g_pairs = g_M + (MG ? MB : 0);  // stage-pair kernels T (9) + cpp (1)
     static constexpr int g_save = g_pairs + NPAIR * 10;  // copy of the a_* region
     static constexpr int g_total = (g_save + (a_end - o_work) + 1) & ~1;
 };
@@ -380,12 +383,12 @@ struct TickLayout {
 // lockstep by one mbarrier arrival per iteration so that the warps of an SM run the same code at
 // about the same time and share instruction-cache lines (the kernel is instruction-fetch bound
 // otherwise: profiles/r1_summary.md).
-template <int HZ, int SMAX, int LB, int NT, int NW>
+template <int HZ, int SMAX, int LB, int NT, int NW, bool MG = false>
 __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
                                                        const int* __restrict__ work_list,
                                                        const int* __restrict__ work_count,
                                                        double* __restrict__ hscratch) {
-    using L = TickLayout<HZ, SMAX, LB>;
+    using L = TickLayout<HZ, SMAX, LB, MG>;
     constexpr int E = LB * LB, TS = L::TS, NAB = L::NAB;
     constexpr int NPT = (LB * SMAX + NT - 1) / NT;  // variables per thread
     static_assert(NW == 1 || NT == 32, "several robots per CTA only with one warp per robot");
@@ -397,7 +400,9 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
     double* sm = sm_cta + (size_t)wid * per_group;
     uint64_t* lockbar = reinterpret_cast<uint64_t*>(sm_cta + (size_t)NW * per_group);  // CTA-wide lockstep barrier
 
-    double* Mb = sm + L::o_M;
+    // per-group scratch in global memory: plain (coherent) loads/stores, ordered by the group barrier
+    double* gbase = hscratch + (size_t)group * L::g_total;
+    double* Mb = MG ? gbase + L::g_M : sm + L::o_M;
     double* s_in = sm + L::o_in;
     double* gv = sm + L::o_g;
     double* uv = sm + L::o_u;
@@ -447,8 +452,6 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
             if (tid == 0) asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" ::"r"(smem_u32(lockbar)) : "memory");
         }
     };
-    // per-group scratch in global memory: plain (coherent) loads/stores, ordered by the group barrier
-    double* gbase = hscratch + (size_t)group * L::g_total;
     double* hglob = gbase + L::g_H;
     double* pairs = gbase + L::g_pairs;
     double* gsave = gbase + L::g_save;
@@ -909,6 +912,17 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
         // H is in Mb (h_valid) or on its way (h_pending)
         bool h_valid = true, h_pending = false;
         auto h_issue = [&]() {  // all threads: make Mb reusable, then one lane issues the bulk copy
+            if constexpr (MG) {  // matrix in global memory: a plain cooperative copy H -> working copy
+                gsync<NT>();
+                const int nd2 = (S * (S + 1) / 2) * TS / 2;
+                const double2* src = reinterpret_cast<const double2*>(hglob);
+                double2* dst = reinterpret_cast<double2*>(Mb);
+                for (int i = tid; i < nd2; i += NT) dst[i] = src[i];
+                gsync<NT>();
+                h_pending = false;
+                h_valid = true;
+                return;
+            }
             asm volatile("fence.proxy.async;" ::: "memory");
             gsync<NT>();
             if (tid == 0) {

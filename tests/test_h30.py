@@ -1,0 +1,60 @@
+"""Horizon 30 (BASELINE.json configs[3]): larger per-instance factor.  Standing has a reference-defined answer
+(known answer G5); walking uses the periodic gait extension (new behaviour behind ``extend_gait``:
+the reference raises IndexError there, MPC.py:58).  Both are checked against the oracle's certified optimum."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+U_RTOL = 1e-4     # north_star
+TAU_ATOL = 1e-4   # north_star [N*m]
+
+
+def test_h30_known_answer_g5_and_random_instances():
+    import torch
+    from oracle import reference_mpc as rm
+    from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
+    assert torch.cuda.is_available()
+    mpc_o, biped_o = rm.MPCParams(h=30), rm.BipedParams()
+    mpc = MPC(h=30)
+    s = BatchedMPC(mpc, Biped(), max_batch=32, extend_gait=True)
+    # G5: the reference script's default state, standing, h = 30
+    pf = rm.getFootPositionWorld(rm.X_FB0, rm.Q0, biped_o).reshape(1, 6)
+    out = s.step_host(rm.X_FB0[None], np.zeros(1), pf, np.ones((1, 30, 2), dtype=np.uint8), rm.Q0[None], rm.QD0[None], pf)
+    assert out["status"][0] == 0
+    u0 = out["controls"][0, 0]
+    np.testing.assert_allclose([u0[2], u0[5]], [80.27621019, 80.27621019], rtol=1e-8)
+    np.testing.assert_allclose([u0[7], u0[10]], [-1.598819615, -1.598819615], rtol=1e-8)
+    # random instances: walking (extended gait) and standing
+    n = 10
+    b = synth.make_batch(n, shard_index=11, mpc=mpc, extend=True, walking_prob=0.6)
+    out = s.step_host(b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"], phase_k=b["phase_k"],
+                      want_states=True)
+    assert (out["status"] == 0).all(), (out["status"], out["iters"])
+    assert set(b["gait"].tolist()) == {0, 1}
+    for i in range(n):
+        st, ct = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc_o, biped_o, b["contact"][i], extend=True)
+        tau = rm.lowLevelControl(b["x_fb"][i], float(b["t"][i]), b["pf_w"][i].reshape(6, 1), b["q"][i], b["qd"][i], mpc_o,
+                                 biped_o, b["contact"][i], ct[0].reshape(-1, 1)).reshape(-1)
+        scale = max(1.0, np.abs(ct).max())
+        assert np.abs(out["controls"][i] - ct).max() / scale <= U_RTOL, i
+        assert np.abs(out["states"][i] - st).max() <= 1e-6 * max(1.0, np.abs(st).max()), i
+        assert np.abs(out["tau"][i] - tau).max() <= TAU_ATOL, i
+    s.close()
+
+
+def test_h30_batch_all_certified_and_split_invariant():
+    """4,096 horizon-30 instances: every one certified optimal; results do not depend on the batch split."""
+    import torch
+    from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
+    mpc = MPC(h=30)
+    n = 4096
+    b = synth.make_batch(n, shard_index=12, mpc=mpc, extend=True)
+    s = BatchedMPC(mpc, Biped(), max_batch=n, extend_gait=True)
+    args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+    full = s.step_host(*args, phase_k=b["phase_k"])
+    assert (full["status"] == 0).all(), np.bincount(full["status"], minlength=4)
+    half = s.step_host(*[a[:n // 2] for a in args], phase_k=b["phase_k"][:n // 2])
+    np.testing.assert_array_equal(half["controls"], full["controls"][:n // 2])
+    np.testing.assert_array_equal(half["tau"], full["tau"][:n // 2])
+    s.close()
