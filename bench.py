@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="instances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short h=30 and closed-loop rollout legs")
     return ap.parse_args()
 
 
@@ -159,6 +160,60 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, measured briefly after the headline (reported under "other_configs")
+# ------------------------------------------------------------------------------------------
+def other_configs(torch, dev, local_rank, rank, world, barrier, max_over_ranks, sum_over_ranks):
+    from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
+    tn = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    out = {}
+
+    def timed(fn, reps):
+        fn()  # warm-up (allocations, first launch)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps, r
+
+    # configs[3]: horizon 30 (periodic gait extension for the walking instances; standing is reference-defined)
+    n30 = 8192
+    mpc30 = MPC(h=30)
+    b = synth.make_batch(n30, shard_index=1000 + rank, mpc=mpc30, extend=True)
+    s30 = BatchedMPC(mpc30, Biped(), max_batch=n30, device=local_rank, extend_gait=True)
+    d = [tn(b["x_fb"]), tn(b["phase_k"], torch.int32), tn(b["t"]), tn(b["foot"]), tn(b["contact"], torch.uint8),
+         tn(b["q"]), tn(b["qd"]), tn(b["pf_w"])]
+    ms, r = timed(lambda: s30.step(*d), 2)
+    st = r["status"].cpu().numpy()
+    out["h30"] = {"workload": f"{n30} horizon-30 ticks per GPU (BASELINE.json configs[3]; 85% walking with the periodic gait "
+                              "extension, 15% standing)", "solves_per_s": world * n30 / (ms * 1e-3), "ms_per_step": ms,
+                  "mean_iters": float(r["iters"].float().mean().item()),
+                  "not_optimal": int(sum_over_ranks(float((st != 0).sum())))}
+    s30.close()
+
+    # configs[4]: closed-loop rollout (MPC + J^T torques + SRB plant, rules R1-R7 of DESIGN.md 9)
+    nr, ticks = 16384, 100
+    sr = BatchedMPC(MPC(), synth.rollout_biped(), max_batch=nr, device=local_rank)
+    rb = synth.make_rollout_batch(nr, shard_index=rank)
+    for mode, warm in (("warm", True), ("cold", False)):
+        def run():
+            stt = [tn(rb["x"]), tn(rb["foot"]), tn(rb["tick"], torch.int32), tn(rb["gait"], torch.uint8), tn(rb["q"]), tn(rb["qd"])]
+            return sr.rollout(*stt, ticks, warm_start=warm)
+        ms, r = timed(run, 1)
+        sn = BatchedMPC.rollout_stats(r["stats"])
+        out["rollout_" + mode] = {"workload": f"{nr} robots x {ticks} ticks per GPU, closed loop (BASELINE.json configs[4] at a "
+                                              f"tenth of its 1,000 ticks), warm_start={warm}; includes the H2D of the initial states",
+                                  "robot_ticks_per_s": world * nr * ticks / (ms * 1e-3), "ms_per_tick": ms / ticks,
+                                  "mean_iters": sn["mean_iters"], "warm_hit_rate": sn["warm_hit_rate"],
+                                  "not_optimal": int(sum_over_ranks(float(sn["not_optimal"]))),
+                                  "falls": int(sum_over_ranks(float(sn["falls"])))}
+    sr.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def run_b200(args, rank, local_rank, world):
@@ -182,6 +237,12 @@ def run_b200(args, rank, local_rank, world):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
     mpc, biped = MPC(), Biped()
@@ -230,14 +291,20 @@ def run_b200(args, rank, local_rank, world):
     fl = batch_flops(batch["contact"], iters)
     peaks = measure(local_rank)
     kernels = []
-    for cls, name in ((0, "mpc_tick2_kernel<10,10,5,32> (<=10 stance foot-stages: walking class, one warp per robot)"),
-                      (1, "mpc_tick2_kernel<10,20,5,128> (11..20 stance foot-stages: standing class, one CTA per robot)")):
+    for cls, name in ((0, "mpc_tick2_kernel<10,10,5,32,5> (<=10 stance foot-stages: walking class, one warp per robot, 5 robots per CTA)"),
+                      (1, "mpc_tick2_kernel<10,20,5,128,1> (11..20 stance foot-stages: standing class, one CTA per robot)")):
         ach = fl[cls] / (kt[1 + cls] * 1e-3) / 1e12 if kt[1 + cls] > 0 else 0.0
         kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
                         "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"]})
     dom = int(np.argmax(kt[1:]))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from one ncu capture of this batch size
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if int(tj.get("batch", -1)) == n:
+            traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
     roofline = {"bound": "fp64_fma", "achieved": kernels[dom]["achieved_tflops"], "peak": peaks["fp64_fma_tflops"],
-                "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": None,
+                "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": traffic,
                 "peak_source": "measured in this run by bmpc_measure_fma_peak (register-resident DFMA chains on all SMs); "
                                "MEASURED_PEAKS.json carries no FP64 CUDA-core figure",
                 "fp32_fma_peak_tflops": peaks["fp32_fma_tflops"], "dominant_kernel": kernels[dom]["kernel"],
@@ -265,6 +332,10 @@ def run_b200(args, rank, local_rank, world):
     from biped_mpc_py_b200.shard import local_stats, reduce_stats
     stats = reduce_stats(*local_stats(status, iters, resid), device=dev)
 
+    extra = None
+    if not args.no_extra:
+        extra = other_configs(torch, dev, local_rank, rank, world, barrier, max_over_ranks, sum_over_ranks)
+
     line = None
     if rank == 0:
         # single-instance latency through the reference-signature path (N=1, launch + copies + sync)
@@ -290,7 +361,7 @@ def run_b200(args, rank, local_rank, world):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "latency": latency,
+                "cpu_baseline": cpu, "latency": latency, "other_configs": extra,
                 "solver": {"mean_iters": float(stats["mean_iters"]), "max_iters": int(stats["iters_max"]),
                            "not_optimal": int(stats["not_optimal"]), "bad_input": int(stats["bad_input"]),
                            "max_mu": float(stats["mu_max"]), "max_rd": float(stats["rd_max"]),
