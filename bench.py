@@ -17,6 +17,8 @@ import os
 
 for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")  # the CPU legs run one process per core
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its banner on stdout; rank 0 must print exactly one JSON line
 
 import argparse
 import json
