@@ -95,6 +95,9 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     d.gondzio = 1;
     d.init_fz_frac = 0.2;   // start point: 20 % of the fz range, friction/moment components centred
     d.mu0_scale = 0.1;      // initial complementarity = mu0_scale * mean slack
+    // polish rounds per attempt: long horizons have more weakly active rows that only show up as violations
+    // one round at a time (h = 30 instances needing 5-7 rounds were measured with tools/kernel_model.py)
+    d.polish_rounds = P.h > 10 ? 8 : 4;
     d.warm_rounds = 6;      // polish rounds allowed to a warm-started tick before it falls back to the cold path
     d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
     memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));

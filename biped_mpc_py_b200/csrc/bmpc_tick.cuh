@@ -978,14 +978,16 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     }
                     ++it;
                     lock_sync();
-                    h_need();
                     part = 0.0;
                     BMPC_FOR_ROWS(r, j, k) {
                         const double s = r_s[r], l = r_l[r];
-                        r_d[r] = l / s;
-                        r_p[r] = cdot(j, k, uv) + s - rb[k];
+                        const double d = l / s, rp = cdot(j, k, uv) + s - rb[k];
+                        r_d[r] = d;
+                        r_p[r] = rp;
+                        r_w[r] = d * rp - l;  // predictor right-hand side row term (used below)
                         part += s * l;
                     }
+                    h_need();  // H back in Mb (its reload was issued right after the last solve of the previous iteration)
                     gsync<NT>();
                     if (!rd_fresh) {
                         // stationarity residual rd = Hc u + g + C' lam, evaluated once; a Newton step of
@@ -1008,7 +1010,6 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         break;
                     }
                     // M = Hc + blockdiag(Cb' diag(d_j) Cb); predictor rhs = -rd - C'(d rp - lam)
-                    BMPC_FOR_ROWS(r, j, k) r_w[r] = r_d[r] * r_p[r] - r_l[r];
 #pragma unroll 1
                     for (int e = tid; e < S * NAB; e += NT) {
                         const int j = e / NAB, ab = e - j * NAB;
@@ -1092,6 +1093,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_w);
                         gsync<NT>();
                         tile_solve<LB, NT, NPT>(Mb, S, xv);
+                        h_issue();  // the factor is dead: bring H back while the step length and the update are computed
                         ratio = 0.f;
                         BMPC_FOR_ROWS(r, j, k) {
                             const double cx = cdot(j, k, xv);
@@ -1120,7 +1122,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) uv[i] += alpha * duv[i], rdv[i] *= (1.0 - alpha);
                     rdmax *= (1.0 - alpha);
-                    h_issue();  // (syncs) bring H back while the next iteration starts
+                    if (!p.gondzio) h_issue();
+                    gsync<NT>();
                 }
 
                 // ============================ active-set polish ============================
@@ -1153,7 +1156,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                 gsync<NT>();
                 }
                 bool ok = false;
-                const int max_rounds = attempt < 0 ? p.warm_rounds : 4;
+                const int max_rounds = attempt < 0 ? p.warm_rounds : p.polish_rounds;
                 for (int round = 0; round < max_rounds; ++round) {
                     lock_sync();
                     // per block: affine set of the active rows  u_b = p_b + N_b w_b

@@ -123,6 +123,37 @@ def test_random_batch_against_oracle(torch_cuda):
     solver.close()
 
 
+def test_config1_4096_instances_each_against_oracle(torch_cuda):
+    """BASELINE.json configs[1]: 4,096 independent horizon-10 QPs from randomised states on one B200, EVERY instance
+    checked against the oracle's certified optimum (the oracle runs on all host cores, ~40 ms per instance)."""
+    from biped_mpc_py_b200 import synth
+    from oracle_pool import oracle_parallel
+    n = 4096
+    solver, mpc, biped = _solver(0, max_batch=n)
+    batch = synth.make_batch(n, shard_index=2, mpc=mpc, biped=biped)
+    out = solver.step_host(batch["x_fb"], batch["t"], batch["foot"], batch["contact"], batch["q"], batch["qd"], batch["pf_w"])
+    U, T, M = oracle_parallel(batch, n)
+    assert (out["status"] == 0).all(), np.bincount(out["status"])
+    scale = np.maximum(1.0, np.abs(U).reshape(n, -1).max(axis=1))
+    du = np.abs(out["controls"] - U).reshape(n, -1).max(axis=1) / scale
+    dtau = np.abs(out["tau"] - T).max(axis=1)
+    assert du.max() <= U_RTOL and dtau.max() <= TAU_ATOL, (du.max(), dtau.max())   # north_star tolerances
+    assert du.max() <= U_RTOL_TIGHT, du.max()
+    # same active friction-cone set: rows may differ only within 10x the activity threshold (SURVEY.md 7.7)
+    differ = out["fric_active"] != M
+    n_differ = 0
+    for i, s in zip(*np.nonzero(differ)):
+        u, tol, near = U[i, s], 1e-6 * scale[i], False
+        for leg in range(2):
+            fx, fy, fz = u[3 * leg:3 * leg + 3]
+            res = np.array([fx - biped.mu * fz, fy - biped.mu * fz, -fx - biped.mu * fz, -fy - biped.mu * fz])
+            near = near or (np.abs(res + tol) < 10 * tol).any() or abs(fz - tol) < 10 * tol
+        assert near, (i, s, out["fric_active"][i, s], M[i, s])
+        n_differ += 1
+    assert n_differ <= n // 100
+    solver.close()
+
+
 def test_device_api_matches_host_api_and_is_shard_invariant(torch_cuda):
     """Device-tensor API == host API bit for bit; splitting the batch changes nothing."""
     torch = torch_cuda
