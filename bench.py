@@ -17,8 +17,10 @@ import os
 
 for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")  # the CPU legs run one process per core
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its banner on stdout; rank 0 must print exactly one JSON line
+if not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
+    # NCCL prints its version banner on STDOUT at VERSION level and above (the level can also come from
+    # /etc/nccl.conf); rank 0 must print exactly one JSON line, so debug output goes to stderr's file instead
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import argparse
 import json
@@ -228,7 +230,20 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to STDOUT when the communicator is created; rank 0 must print exactly one
+        # JSON line, so file descriptor 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:
