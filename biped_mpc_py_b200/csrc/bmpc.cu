@@ -53,8 +53,9 @@ struct bmpc_handle {
     bmpc_params host_params;
     DevParams dp;
     Variant bucket[2];
-    int* d_lists = nullptr;   // [2][max_batch]
-    int* d_counts = nullptr;  // [2]
+    Variant fallback;         // dense re-solve of instances the stage-wise class-1 kernel did not certify (h = 30), or empty
+    int* d_lists = nullptr;   // [3][max_batch]: two classes + the fallback list
+    int* d_counts = nullptr;  // [3]
     int64_t launches = 0;
     // closed-loop rollout workspace (allocated on the first bmpc_rollout call, max_batch sized)
     struct {
@@ -97,7 +98,7 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     d.mu0_scale = 0.1;      // initial complementarity = mu0_scale * mean slack
     // polish rounds per attempt: long horizons have more weakly active rows that only show up as violations
     // one round at a time (h = 30 instances needing 5-7 rounds were measured with tools/kernel_model.py)
-    d.polish_rounds = P.h > 10 ? 8 : 4;
+    d.polish_rounds = P.h > 10 ? 16 : 4;
     d.warm_rounds = 6;      // polish rounds allowed to a warm-started tick before it falls back to the cold path
     d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
     memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));
@@ -162,10 +163,10 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     return 0;
 }
 
-template <int HZ, int SMAX, int LB, int NT, int NW, bool MG = false>
+template <int HZ, int SMAX, int LB, int NT, int NW, bool MG = false, bool RIC = false>
 int setup_variant(Variant& v, int num_sms, int mb) {
-    using L = TickLayout<HZ, SMAX, LB, MG>;
-    v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT, NW, MG>;
+    using L = TickLayout<HZ, SMAX, LB, MG, RIC>;
+    v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT, NW, MG, RIC>;
     v.smem = L::bytes(mb) * NW + 16;  // + the CTA-wide lockstep mbarrier
     v.threads = NT * NW;
     v.per_cta = NW;
@@ -185,7 +186,7 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
                  (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
-    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 3 * sizeof(int), st));
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
@@ -195,6 +196,14 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         const int grid = (std::min(n, v.resident) + v.per_cta - 1) / v.per_cta;
         v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b,
                                                v.d_scratch);
+        if (b == 1 && h->fallback.fn) {
+            const Variant& f = h->fallback;
+            collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_lists + (size_t)h->max_batch, h->d_counts + 1, io.status,
+                                                                       h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2);
+            const int fgrid = (std::min(n, f.resident) + f.per_cta - 1) / f.per_cta;
+            f.fn<<<fgrid, f.threads, f.smem, st>>>(h->dp, io, h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2, f.d_scratch);
+            h->launches += 2;
+        }
         if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2 + b], st));
     }
     h->launches += 3;
@@ -241,8 +250,21 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
             delete h;
             return fail("h = 30 is instantiated for the reference limit structure only (exactly one pinned component)");
         }
-        rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
-             setup_variant<30, 60, 5, 256, 1, true>(h->bucket[1], h->num_sms, h->dp.mb);
+        // walking class (<= 30 stance foot-stages): dense tile factor in shared memory (97 KB).  Standing class (<= 60):
+        // stage-wise Riccati backend (no 380 KB matrix), with a dense re-solve (matrix in the L2 scratch) of the few
+        // instances it does not certify.  BMPC_H30=dense / ric force one backend for both classes (experiments).
+        const char* er = getenv("BMPC_H30");
+        const std::string mode = er ? er : "hybrid";
+        if (mode == "dense")
+            rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
+                 setup_variant<30, 60, 5, 256, 1, true>(h->bucket[1], h->num_sms, h->dp.mb);
+        else if (mode == "ric")
+            rc = setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], h->num_sms, h->dp.mb) ||
+                 setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb);
+        else
+            rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
+                 setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb) ||
+                 setup_variant<30, 60, 5, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
     } else if (h->dp.LB == 5) {
         rc = (nww == 1 ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
                          : setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)) ||
@@ -256,8 +278,8 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         delete h;
         return 1;
     }
-    e = cudaMalloc(&h->d_lists, sizeof(int) * 2 * (size_t)max_batch);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 2);
+    e = cudaMalloc(&h->d_lists, sizeof(int) * 3 * (size_t)max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 3);
     if (e != cudaSuccess) {
         cudaFree(h->d_lists);
         delete h;
@@ -273,6 +295,7 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaFree(h->d_lists);
     cudaFree(h->d_counts);
     for (int b = 0; b < 2; ++b) cudaFree(h->bucket[b].d_scratch);
+    cudaFree(h->fallback.d_scratch);
     cudaFree(h->ro.contact), cudaFree(h->ro.phase_k), cudaFree(h->ro.t_swing), cudaFree(h->ro.controls);
     cudaFree(h->ro.tau), cudaFree(h->ro.status), cudaFree(h->ro.iters), cudaFree(h->ro.ws_mask);
     for (int i = 0; i < 4; ++i)

@@ -1,0 +1,429 @@
+// Stage-wise (Riccati) linear-algebra backend of the tick kernel.
+//
+// The contact-reduced QP is an LQR problem in disguise:  X_k = A_k X_{k-1} + B_k u_k (+ const) with
+// A_k = I + dt E_k (theta += dt Rinv_k omega, p += dt v; MPC.py:165-171, 183) and B_k non-zero only in the
+// omega rows (Bw = dt Iw^-1 [skew(r) | I]) and the v rows (Bv = dt/m [I | 0]) (MPC.py:174-184), cost
+// 1/2 sum_k (X_k - xref_k)' Q (X_k - xref_k) + 1/2 u_k' R u_k (MPC.py:277-286).  Every system the interior point
+// and the polish solve has the form (Hc - blockdiag(Rb) + blockdiag(Rt_j)) du = rhs with per-block Rt_j, i.e.
+// the same LQR with modified input weights, so ONE backward Riccati sweep factors it and a backward + forward
+// sweep solves each right-hand side: O(h) work and storage instead of the O(h^3) / O(h^2) of the dense
+// condensed factor.  Products Hc v + g and diag(Hc) are evaluated without forming Hc (rollout + adjoint,
+// uncontrolled cost-to-go).  Model and derivation: tools/riccati_model.py (checked against the dense form).
+//
+// Used for horizon 30 (BASELINE.json configs[3]), where the dense tile matrix is 97 KB / 380 KB per robot.
+#pragma once
+#include "bmpc_kernels.cuh"
+
+namespace bmpc {
+
+template <int NT>
+__device__ __forceinline__ void rsync() {
+    if constexpr (NT == 32) __syncwarp();
+    else __syncthreads();
+}
+
+// Shared-memory view of one robot's Riccati data (all pointers into the group's shared memory)
+template <int LB>
+struct Ric {
+    static constexpr int NU = 2 * LB;  // inputs per stage: at most two stance feet
+    double* K;     // [S][LB][12]   feedback rows of the block's inputs (K = Ginv F)
+    double* Gi;    // [S][LB][NU]   the block's rows of inv(G_k)
+    double* W0;    // [S][3][LB]    omega rows of B for the block (problem data)
+    double* Bw;    // [S][3][LB]    effective omega rows (= W0, or W0 N in the polish)
+    double* Bv;    // [S][3][LB]    effective v rows (= dt/m selector, or that times N)
+    double* rinv;  // [HZ][9]
+    double* err;   // [HZ][12]      free response minus reference
+    double* et;    // [HZ][12]      trajectory scratch of the gradient
+    double* P;     // [12][12]
+    double* PA;    // [12][12]
+    double* PB;    // [12][NU]
+    double* F;     // [NU][12]
+    double* G;     // [NU][NU]
+    double* vec;   // [64]: p/dx double buffers (2 x 12), A'p / A dx (12), t (NU)
+    const int* sfirst;  // [HZ] first block of the stage
+    const int* scnt;    // [HZ] blocks in the stage (0, 1, 2)
+    const int* blk_foot;
+    int HZ;
+    double dt, vm;  // vm = dt / mass
+
+    static constexpr int per_block = LB * 12 + LB * NU + 3 * 3 * LB;
+    __host__ __device__ static constexpr int doubles(int hz, int smax) {
+        return smax * per_block + hz * (9 + 12 + 12) + 2 * 144 + 12 * NU + NU * 12 + NU * NU + 64;
+    }
+    __device__ void carve(double* base, int hz, int smax) {
+        K = base;
+        Gi = K + smax * LB * 12;
+        W0 = Gi + smax * LB * NU;
+        Bw = W0 + smax * 3 * LB;
+        Bv = Bw + smax * 3 * LB;
+        rinv = Bv + smax * 3 * LB;
+        err = rinv + hz * 9;
+        et = err + hz * 12;
+        P = et + hz * 12;
+        PA = P + 144;
+        PB = PA + 144;
+        F = PB + 12 * NU;
+        G = F + NU * 12;
+        vec = G + NU * NU;
+        HZ = hz;
+    }
+};
+
+// block-diagonal input weight Rt_j(a, b): interior point  Rb + Cb' diag(d_j) Cb,  polish  N_j' Rb N_j (+ I on the padding)
+struct RtSpec {
+    int polish;
+    const double* Cb;   // [mb][LB]
+    const double* dd;   // [S*mb] barrier weights lam/s
+    int mb;
+    const double* Nn;   // [S][LB*LB] null-space blocks (component c, basis vector a at c*LB + a)
+    const int* bdim;    // [S]
+};
+
+template <int LB>
+__device__ __forceinline__ double block_R(const DevParams& p, int foot, int c) {  // R entry of free component c (MPC.py:28)
+    const int ca = p.comps[c];
+    return p.R[(ca < 3) ? (3 * foot + ca) : (6 + 3 * foot + ca - 3)];
+}
+
+template <int LB>
+__device__ __forceinline__ double rt_entry(const DevParams& p, const RtSpec& rt, int j, int foot, int a, int b) {
+    double acc = 0.0;
+    if (!rt.polish) {
+        if (a == b) acc = block_R<LB>(p, foot, a);
+        const double* dd = rt.dd + j * rt.mb;
+#pragma unroll 1
+        for (int k = 0; k < rt.mb; ++k) acc += rt.Cb[k * LB + a] * rt.Cb[k * LB + b] * dd[k];
+    } else {
+        const double* N = rt.Nn + j * LB * LB;
+#pragma unroll
+        for (int c = 0; c < LB; ++c) acc += N[c * LB + a] * block_R<LB>(p, foot, c) * N[c * LB + b];
+        if (a == b && a >= rt.bdim[j]) acc += 1.0;
+    }
+    return acc;
+}
+
+// effective input maps: interior point (Bw = W0, Bv = dt/m selector) or polish (both times N_j)
+template <int LB, int NT>
+__device__ __noinline__ void ric_set_maps(const DevParams& p, Ric<LB>& r, int S, const double* Nn /* null: interior point */) {
+    const int tid = threadIdx.x & (NT - 1);
+    for (int e = tid; e < S * 3 * LB; e += NT) {
+        const int j = e / (3 * LB), x = (e - j * 3 * LB) / LB, a = e % LB;
+        double bw, bv;
+        if (Nn == nullptr) {
+            bw = r.W0[e];
+            bv = (p.comps[a] == x) ? r.vm : 0.0;
+        } else {
+            const double* N = Nn + j * LB * LB;
+            bw = 0.0, bv = 0.0;
+#pragma unroll
+            for (int c = 0; c < LB; ++c) {
+                bw += r.W0[(j * 3 + x) * LB + c] * N[c * LB + a];
+                if (p.comps[c] == x) bv += r.vm * N[c * LB + a];
+            }
+        }
+        r.Bw[e] = bw;
+        r.Bv[e] = bv;
+    }
+    rsync<NT>();
+}
+
+// PA = P A_k, then P <- Q + A_k' PA - F'K (the F'K term only when nu > 0).  A_k = I + dt E_k.
+template <int LB, int NT>
+__device__ __forceinline__ void ric_step_P(const DevParams& p, Ric<LB>& r, int k, int nu, const double* Kst /* [nu][12] rows via Kptr */,
+                                           int j0) {
+    const int tid = threadIdx.x & (NT - 1);
+    const double* ri = r.rinv + 9 * k;
+    const double dt = r.dt;
+    for (int e = tid; e < 144; e += NT) {
+        const int a = e / 12, b = e - 12 * a;
+        double v = r.P[e];
+        if (b >= 6 && b < 9) v += dt * (r.P[a * 12 + 0] * ri[b - 6] + r.P[a * 12 + 1] * ri[3 + b - 6] + r.P[a * 12 + 2] * ri[6 + b - 6]);
+        if (b >= 9) v += dt * r.P[a * 12 + 3 + b - 9];
+        r.PA[e] = v;
+    }
+    rsync<NT>();
+    // lower triangle, mirrored: keeps P exactly symmetric
+    for (int e = tid; e < 78; e += NT) {
+        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        if (a * (a + 1) / 2 > e) --a;
+        if ((a + 1) * (a + 2) / 2 <= e) ++a;
+        const int b = e - a * (a + 1) / 2;  // b <= a
+        double v = r.PA[a * 12 + b];
+        if (a >= 6 && a < 9) v += dt * (ri[a - 6] * r.PA[b] + ri[3 + a - 6] * r.PA[12 + b] + ri[6 + a - 6] * r.PA[24 + b]);
+        if (a >= 9) v += dt * r.PA[(3 + a - 9) * 12 + b];
+        if (a == b) v += p.Q[a];
+#pragma unroll 1
+        for (int c = 0; c < nu; ++c) {
+            const double* Kr = r.K + ((j0 + c / LB) * LB + c % LB) * 12;
+            v -= r.F[c * 12 + a] * Kr[b];
+        }
+        r.P[a * 12 + b] = v;
+        r.P[b * 12 + a] = v;
+    }
+    rsync<NT>();
+}
+
+// Backward Riccati sweep: stores K and inv(G) rows per block.  Uniform return value (false: a pivot was not positive).
+template <int LB, int NT>
+__device__ __noinline__ bool ric_factor(const DevParams& p, Ric<LB>& r, const RtSpec& rt) {
+    constexpr int NU = 2 * LB;
+    const int tid = threadIdx.x & (NT - 1);
+    for (int e = tid; e < 144; e += NT) r.P[e] = (e / 12 == e % 12) ? p.Q[e / 12] : 0.0;
+    rsync<NT>();
+    bool ok = true;
+    for (int k = r.HZ - 1; k >= 0; --k) {
+        const int cnt = r.scnt[k], j0 = r.sfirst[k], nu = cnt * LB;
+        if (cnt > 0) {
+            // PB = P B_k
+            for (int e = tid; e < 12 * nu; e += NT) {
+                const int a = e / nu, c = e - a * nu, j = j0 + c / LB, cc = c % LB;
+                const double* bw = r.Bw + j * 3 * LB + cc;
+                const double* bv = r.Bv + j * 3 * LB + cc;
+                const double* Pa = r.P + a * 12;
+                r.PB[a * NU + c] = Pa[6] * bw[0] + Pa[7] * bw[LB] + Pa[8] * bw[2 * LB] + Pa[9] * bv[0] + Pa[10] * bv[LB] + Pa[11] * bv[2 * LB];
+            }
+            rsync<NT>();
+            // G = Rt + B_k' PB ;  F = PB' A_k
+            for (int e = tid; e < nu * nu; e += NT) {
+                const int rr = e / nu, c = e - rr * nu, jr = j0 + rr / LB, ra = rr % LB, jc = j0 + c / LB;
+                const double* bw = r.Bw + jr * 3 * LB + ra;
+                const double* bv = r.Bv + jr * 3 * LB + ra;
+                double v = bw[0] * r.PB[6 * NU + c] + bw[LB] * r.PB[7 * NU + c] + bw[2 * LB] * r.PB[8 * NU + c] +
+                           bv[0] * r.PB[9 * NU + c] + bv[LB] * r.PB[10 * NU + c] + bv[2 * LB] * r.PB[11 * NU + c];
+                if (jr == jc) v += rt_entry<LB>(p, rt, jr, r.blk_foot[jr], ra, c % LB);
+                r.G[rr * NU + c] = v;
+            }
+            if (k > 0) {
+                const double* ri = r.rinv + 9 * k;
+                for (int e = tid; e < nu * 12; e += NT) {
+                    const int c = e / 12, a = e - 12 * c;
+                    double v = r.PB[a * NU + c];
+                    if (a >= 6 && a < 9)
+                        v += r.dt * (r.PB[0 * NU + c] * ri[a - 6] + r.PB[1 * NU + c] * ri[3 + a - 6] + r.PB[2 * NU + c] * ri[6 + a - 6]);
+                    if (a >= 9) v += r.dt * r.PB[(3 + a - 9) * NU + c];
+                    r.F[c * 12 + a] = v;
+                }
+            }
+            rsync<NT>();
+            // in-place Gauss-Jordan inversion of the SPD nu x nu matrix G (no pivoting needed)
+            for (int pv = 0; pv < nu; ++pv) {
+                const double gpp = r.G[pv * NU + pv];
+                ok = ok && (gpp > 0.0) && (gpp < 1e300);
+                const double d = 1.0 / gpp;
+                double nv[(NU * NU + NT - 1) / NT];
+                int q = 0;
+                for (int e = tid; e < nu * nu; e += NT, ++q) {
+                    const int i = e / nu, j = e - i * nu;
+                    const double gij = r.G[i * NU + j], gip = r.G[i * NU + pv], gpj = r.G[pv * NU + j];
+                    nv[q] = (i == pv) ? ((j == pv) ? d : gpj * d) : ((j == pv) ? -gip * d : gij - gip * gpj * d);
+                }
+                rsync<NT>();
+                q = 0;
+                for (int e = tid; e < nu * nu; e += NT, ++q) r.G[(e / nu) * NU + (e % nu)] = nv[q];
+                rsync<NT>();
+            }
+            if (!ok) return false;  // uniform: every thread saw the same pivots
+            // store the rows of inv(G); K = inv(G) F
+            for (int e = tid; e < nu * nu; e += NT) {
+                const int rr = e / nu, c = e - rr * nu;
+                r.Gi[((j0 + rr / LB) * LB + rr % LB) * NU + c] = r.G[rr * NU + c];
+            }
+            if (k > 0) {
+                for (int e = tid; e < nu * 12; e += NT) {
+                    const int rr = e / 12, a = e - 12 * rr;
+                    double v = 0.0;
+#pragma unroll 1
+                    for (int c = 0; c < nu; ++c) v += r.G[rr * NU + c] * r.F[c * 12 + a];
+                    r.K[((j0 + rr / LB) * LB + rr % LB) * 12 + a] = v;
+                }
+            }
+            rsync<NT>();
+        }
+        if (k > 0) ric_step_P<LB, NT>(p, r, k, nu, r.K, j0);
+    }
+    return ok;
+}
+
+// x <- inv(M) x with the factor of ric_factor (x: LB*S entries in shared memory, block order)
+template <int LB, int NT>
+__device__ __noinline__ void ric_solve(Ric<LB>& r, double* __restrict__ x) {
+    constexpr int NU = 2 * LB;
+    const int tid = threadIdx.x & (NT - 1);
+    double* pv = r.vec;        // [12] adjoint
+    double* pn = r.vec + 12;   // [12] next
+    double* tv = r.vec + 36;   // [NU]
+    for (int a = tid; a < 12; a += NT) pv[a] = 0.0;
+    rsync<NT>();
+    // backward: t_k = -rhs_k + B_k' p,  d_k = inv(G_k) t_k (stored in x),  p <- A_k' p - K_k' t_k
+    for (int k = r.HZ - 1; k >= 0; --k) {
+        const int cnt = r.scnt[k], j0 = r.sfirst[k], nu = cnt * LB;
+        if (cnt > 0) {
+            for (int c = tid; c < nu; c += NT) {
+                const int j = j0 + c / LB, cc = c % LB;
+                const double* bw = r.Bw + j * 3 * LB + cc;
+                const double* bv = r.Bv + j * 3 * LB + cc;
+                tv[c] = -x[j0 * LB + c] + bw[0] * pv[6] + bw[LB] * pv[7] + bw[2 * LB] * pv[8] + bv[0] * pv[9] + bv[LB] * pv[10] +
+                        bv[2 * LB] * pv[11];
+            }
+            rsync<NT>();
+            for (int c = tid; c < nu; c += NT) {
+                const double* gi = r.Gi + ((j0 + c / LB) * LB + c % LB) * NU;
+                double v = 0.0;
+#pragma unroll 1
+                for (int q = 0; q < nu; ++q) v += gi[q] * tv[q];
+                x[j0 * LB + c] = v;
+            }
+        }
+        if (k > 0) {
+            const double* ri = r.rinv + 9 * k;
+            for (int a = tid; a < 12; a += NT) {
+                double v = pv[a];
+                if (a >= 6 && a < 9) v += r.dt * (ri[a - 6] * pv[0] + ri[3 + a - 6] * pv[1] + ri[6 + a - 6] * pv[2]);
+                if (a >= 9) v += r.dt * pv[3 + a - 9];
+#pragma unroll 1
+                for (int c = 0; c < nu; ++c) v -= r.K[((j0 + c / LB) * LB + c % LB) * 12 + a] * tv[c];
+                pn[a] = v;
+            }
+            rsync<NT>();
+            double* t = pv;
+            pv = pn;
+            pn = t;
+        } else {
+            rsync<NT>();
+        }
+    }
+    // forward: du_k = -K_k dx_{k-1} - d_k,  dx_k = A_k dx_{k-1} + B_k du_k
+    double* dx = r.vec;
+    double* dn = r.vec + 12;
+    for (int a = tid; a < 12; a += NT) dx[a] = 0.0;
+    rsync<NT>();
+    for (int k = 0; k < r.HZ; ++k) {
+        const int cnt = r.scnt[k], j0 = r.sfirst[k], nu = cnt * LB;
+        if (cnt > 0) {
+            for (int c = tid; c < nu; c += NT) {
+                double v = -x[j0 * LB + c];
+                if (k > 0) {
+                    const double* Kr = r.K + ((j0 + c / LB) * LB + c % LB) * 12;
+#pragma unroll
+                    for (int a = 0; a < 12; ++a) v -= Kr[a] * dx[a];
+                }
+                x[j0 * LB + c] = v;
+            }
+            rsync<NT>();
+        }
+        if (k + 1 < r.HZ || true) {
+            const double* ri = r.rinv + 9 * k;
+            for (int a = tid; a < 12; a += NT) {
+                double v = dx[a];
+                if (k > 0) {
+                    if (a < 3) v += r.dt * (ri[3 * a] * dx[6] + ri[3 * a + 1] * dx[7] + ri[3 * a + 2] * dx[8]);
+                    else if (a < 6) v += r.dt * dx[9 + a - 3];
+                }
+                if (a >= 6) {
+                    const double* bm = (a < 9) ? r.Bw : r.Bv;
+                    const int xr = (a < 9) ? a - 6 : a - 9;
+#pragma unroll 1
+                    for (int c = 0; c < nu; ++c) v += bm[((j0 + c / LB) * 3 + xr) * LB + c % LB] * x[j0 * LB + c];
+                }
+                dn[a] = v;
+            }
+            rsync<NT>();
+            double* t = dx;
+            dx = dn;
+            dn = t;
+        }
+    }
+}
+
+// out = Hc v + g  (rollout of the linear response on top of the free response, then the adjoint sweep)
+template <int LB, int NT>
+__device__ __noinline__ void ric_grad(const DevParams& p, Ric<LB>& r, const double* __restrict__ v, double* __restrict__ out) {
+    const int tid = threadIdx.x & (NT - 1);
+    double* dx = r.vec;
+    double* dn = r.vec + 12;
+    for (int a = tid; a < 12; a += NT) dx[a] = 0.0;
+    rsync<NT>();
+    for (int k = 0; k < r.HZ; ++k) {
+        const int cnt = r.scnt[k], j0 = r.sfirst[k], nu = cnt * LB;
+        const double* ri = r.rinv + 9 * k;
+        for (int a = tid; a < 12; a += NT) {
+            double s = dx[a];
+            if (k > 0) {
+                if (a < 3) s += r.dt * (ri[3 * a] * dx[6] + ri[3 * a + 1] * dx[7] + ri[3 * a + 2] * dx[8]);
+                else if (a < 6) s += r.dt * dx[9 + a - 3];
+            }
+            if (a >= 6) {
+#pragma unroll 1
+                for (int c = 0; c < nu; ++c) {
+                    const int j = j0 + c / LB, cc = c % LB;
+                    const double b = (a < 9) ? r.W0[(j * 3 + a - 6) * LB + cc] : ((p.comps[cc] == a - 9) ? r.vm : 0.0);
+                    s += b * v[j0 * LB + c];
+                }
+            }
+            dn[a] = s;
+            r.et[12 * k + a] = r.err[12 * k + a] + s;
+        }
+        rsync<NT>();
+        double* t = dx;
+        dx = dn;
+        dn = t;
+    }
+    double* av = r.vec;
+    double* an = r.vec + 12;
+    for (int a = tid; a < 12; a += NT) av[a] = 0.0;
+    rsync<NT>();
+    for (int k = r.HZ - 1; k >= 0; --k) {
+        const int cnt = r.scnt[k], j0 = r.sfirst[k], nu = cnt * LB;
+        for (int a = tid; a < 12; a += NT) av[a] += p.Q[a] * r.et[12 * k + a];
+        rsync<NT>();
+        for (int c = tid; c < nu; c += NT) {
+            const int j = j0 + c / LB, cc = c % LB;
+            double s = block_R<LB>(p, r.blk_foot[j], cc) * v[j0 * LB + c] + r.W0[(j * 3 + 0) * LB + cc] * av[6] +
+                       r.W0[(j * 3 + 1) * LB + cc] * av[7] + r.W0[(j * 3 + 2) * LB + cc] * av[8];
+            if (p.comps[cc] < 3) s += r.vm * av[9 + p.comps[cc]];
+            out[j0 * LB + c] = s;
+        }
+        if (k > 0) {
+            const double* ri = r.rinv + 9 * k;
+            for (int a = tid; a < 12; a += NT) {
+                double s = av[a];
+                if (a >= 6 && a < 9) s += r.dt * (ri[a - 6] * av[0] + ri[3 + a - 6] * av[1] + ri[6 + a - 6] * av[2]);
+                if (a >= 9) s += r.dt * av[3 + a - 9];
+                an[a] = s;
+            }
+            rsync<NT>();
+            double* t = av;
+            av = an;
+            an = t;
+        } else {
+            rsync<NT>();
+        }
+    }
+}
+
+// out = diag(Hc): Rb + diag(B_j' Pbar B_j), Pbar = cost-to-go of the uncontrolled system
+template <int LB, int NT>
+__device__ __noinline__ void ric_hdiag(const DevParams& p, Ric<LB>& r, double* __restrict__ out) {
+    const int tid = threadIdx.x & (NT - 1);
+    for (int e = tid; e < 144; e += NT) r.P[e] = (e / 12 == e % 12) ? p.Q[e / 12] : 0.0;
+    rsync<NT>();
+    for (int k = r.HZ - 1; k >= 0; --k) {
+        const int cnt = r.scnt[k], j0 = r.sfirst[k], nu = cnt * LB;
+        for (int c = tid; c < nu; c += NT) {
+            const int j = j0 + c / LB, cc = c % LB;
+            double b[6];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) b[x] = r.W0[(j * 3 + x) * LB + cc], b[3 + x] = (p.comps[cc] == x) ? r.vm : 0.0;
+            double s = block_R<LB>(p, r.blk_foot[j], cc);
+#pragma unroll
+            for (int x = 0; x < 6; ++x)
+#pragma unroll
+                for (int y = 0; y < 6; ++y) s += b[x] * r.P[(6 + x) * 12 + 6 + y] * b[y];
+            out[j0 * LB + c] = s;
+        }
+        rsync<NT>();
+        if (k > 0) ric_step_P<LB, NT>(p, r, k, 0, r.K, 0);
+    }
+}
+
+}  // namespace bmpc

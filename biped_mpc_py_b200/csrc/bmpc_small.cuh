@@ -21,6 +21,18 @@ __global__ void classify_kernel(const uint8_t* __restrict__ contact, int n, int 
     lists[(size_t)b * list_stride + slot] = i;
 }
 
+// instances of a work list that were not certified optimal (and are not bad input): they are re-solved by the
+// dense fallback kernel (the stage-wise backend loses accuracy earlier when barrier weights exceed ~1e10)
+__global__ void collect_uncertified_kernel(const int* __restrict__ list, const int* __restrict__ count,
+                                           const int32_t* __restrict__ status, int* __restrict__ out_list,
+                                           int* __restrict__ out_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    const int inst = list[i];
+    const int st = status[inst];
+    if (st == 1 || st == 2) out_list[atomicAdd(out_count, 1)] = inst;
+}
+
 // lowLevelControl only (MPC.py:444-470): one thread per (instance, leg)
 __global__ void lowlevel_kernel(const __grid_constant__ DevParams p, int n, const double* __restrict__ x_fb,
                                 const double* __restrict__ t_swing, const double* __restrict__ pf_w,

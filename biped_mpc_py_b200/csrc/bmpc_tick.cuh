@@ -15,6 +15,7 @@
 #pragma once
 #include "bmpc_kernels.cuh"
 #include "bmpc_polish.cuh"
+#include "bmpc_riccati.cuh"
 
 namespace bmpc {
 
@@ -319,7 +320,9 @@ __device__ __noinline__ void tile_symv(const double* __restrict__ Mb, int S, con
 // ------------------------------------------------------------------------------------
 // MG: the tile matrix does not fit in shared memory (h = 30 standing: 1,830 tiles, 380 KB) and lives in
 // the per-group global scratch next to H (L2 resident); everything else is unchanged.
-template <int HZ, int SMAX, int LB, bool MG = false>
+// RIC: stage-wise (Riccati) backend (bmpc_riccati.cuh): no tile matrix at all; the o_M region holds the per-block
+// feedback rows, inverse input Hessians and input maps instead.
+template <int HZ, int SMAX, int LB, bool MG = false, bool RIC = false>
 struct TickLayout {
     static constexpr int TS = TileT<LB>::TS;
     static constexpr int N = LB * SMAX;
@@ -330,7 +333,8 @@ struct TickLayout {
     static constexpr int NAB = LB * (LB + 1) / 2;
     // ---- shared memory ----
     static constexpr int o_M = 0;
-    static constexpr int o_in = o_M + (MG ? 0 : MB);   // 2 x IN_DOUBLES TMA destinations (inputs, double buffered)
+    static constexpr int RB = (Ric<LB>::doubles(HZ, SMAX) + 1) & ~1;
+    static constexpr int o_in = o_M + (RIC ? RB : (MG ? 0 : MB));   // 2 x IN_DOUBLES TMA destinations (inputs, double buffered)
     static constexpr int o_g = o_in + 2 * IN_DOUBLES;
     static constexpr int o_u = o_g + NV;
     static constexpr int o_Cb = o_u + NV;
@@ -338,7 +342,7 @@ struct TickLayout {
     static constexpr int o_ub = o_rb + MAXROWS + 2;
     static constexpr int o_red = o_ub + 8;
     static constexpr int o_int = o_red + 16;
-    static constexpr int n_int = 2 * SMAX + 2 * HZ + HZ + 2 * HZ + 2 * SMAX + 16;
+    static constexpr int n_int = 2 * SMAX + 2 * HZ + HZ + 2 * HZ + 2 * SMAX + 16 + 2 * HZ;
     static constexpr int o_bar = ((o_int + (n_int + 1) / 2 + 1) + 1) & ~1;  // mbarriers, 16-byte aligned
     // work region: three n-vectors + 6 row arrays (s, lam, lam/s, rp|ds, wc|dlam, w; run-time sized).
     // The assembly phase, which runs before any of them is live, uses the same region for the
@@ -383,12 +387,12 @@ struct TickLayout {
 // lockstep by one mbarrier arrival per iteration so that the warps of an SM run the same code at
 // about the same time and share instruction-cache lines (the kernel is instruction-fetch bound
 // otherwise: profiles/r1_summary.md).
-template <int HZ, int SMAX, int LB, int NT, int NW, bool MG = false>
+template <int HZ, int SMAX, int LB, int NT, int NW, bool MG = false, bool RIC = false>
 __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
                                                        const int* __restrict__ work_list,
                                                        const int* __restrict__ work_count,
                                                        double* __restrict__ hscratch) {
-    using L = TickLayout<HZ, SMAX, LB, MG>;
+    using L = TickLayout<HZ, SMAX, LB, MG, RIC>;
     constexpr int E = LB * LB, TS = L::TS, NAB = L::NAB;
     constexpr int NPT = (LB * SMAX + NT - 1) / NT;  // variables per thread
     static_assert(NW == 1 || NT == 32, "several robots per CTA only with one warp per robot");
@@ -432,6 +436,14 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
     int* amask = cont + 2 * HZ;       // [SMAX] active-row bit masks (polish)
     int* bdim = amask + SMAX;         // [SMAX] null-space dimension per block
     int* misc = bdim + SMAX;          // [0]=S  [1]=flag
+    int* sfirst = misc + 16;          // [HZ] first block of each stage (Riccati backend)
+    int* scnt = sfirst + HZ;          // [HZ] blocks per stage
+    Ric<LB> ric;
+    if constexpr (RIC) {
+        ric.carve(sm + L::o_M, HZ, SMAX);
+        ric.sfirst = sfirst, ric.scnt = scnt, ric.blk_foot = blk_foot;
+        ric.dt = p.dt, ric.vm = p.dt / p.mass;
+    }
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::o_bar);  // [0],[1] inputs, [2] H reload
 
     const int count = *work_count;
@@ -534,7 +546,9 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
         for (int task = tid; task < 4 + HZ; task += NT) {
             if (task == 0) {
                 int S = 0;  // block list: stance foot-stages in (stage, foot) order
-                for (int s = 0; s < HZ; ++s)
+                for (int s = 0; s < HZ; ++s) {
+                    sfirst[s] = S < SMAX ? S : 0;
+                    scnt[s] = (cont[2 * s] ? 1 : 0) + (cont[2 * s + 1] ? 1 : 0);
                     for (int l = 0; l < 2; ++l) {
                         int b = -1;
                         if (cont[2 * s + l]) {
@@ -543,6 +557,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         }
                         blockOf[2 * s + l] = b;
                     }
+                }
                 misc[0] = S;
             } else if (task == 1) {
                 // next footholds (MPC.py:73-93), including the x_fb[10] quirk of MPC.py:87
@@ -784,7 +799,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
         // ---- 4. condensed Hessian tiles and gradient ---------------------------------------
         {
             const double vm = dt / p.mass;
-            const int ntile = S * (S + 1) / 2;
+            const int ntile = RIC ? 0 : S * (S + 1) / 2;  // the Riccati backend never forms Hc
             for (int t = tid; t < ntile; t += NT) {
                 int jr = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
                 if (jr * (jr + 1) / 2 > t) --jr;
@@ -860,10 +875,15 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
             }
         }
         gsync<NT>();
+        if constexpr (RIC) {  // problem data the stage-wise backend keeps for the whole solve
+            for (int i = tid; i < S * 3 * LB; i += NT) ric.W0[i] = Wm[i];
+            for (int i = tid; i < HZ * 9; i += NT) ric.rinv[i] = rinv[i];
+            for (int i = tid; i < HZ * 12; i += NT) ric.err[i] = err[i];
+        }
         // the assembly arrays are needed again only by the output stage: park them in the scratch
         for (int i = tid; i < L::a_end - L::o_work; i += NT) gsave[i] = sm[L::o_work + i];
         // H -> global scratch (16-byte coalesced stores); TMA brings it back once per iteration
-        {
+        if constexpr (!RIC) {
             const int nd2 = (S * (S + 1) / 2) * TS / 2;
             const double2* src = reinterpret_cast<const double2*>(Mb);
             double2* dst = reinterpret_cast<double2*>(hglob);
@@ -872,7 +892,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
         }
         gsync<NT>();  // the work region changes hands: assembly arrays -> solver vectors / row arrays
         const uint32_t hbytes = (uint32_t)((S * (S + 1) / 2) * TS * 8);
-        if (io.dbg_H != nullptr && w == 0) {
+        if (!RIC && io.dbg_H != nullptr && w == 0) {
             const int nmax = 12 * HZ;
             for (int e = tid; e < n * n; e += NT) {
                 int i = e / n, j = e - i * n;
@@ -912,6 +932,9 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
         // H is in Mb (h_valid) or on its way (h_pending)
         bool h_valid = true, h_pending = false;
         auto h_issue = [&]() {  // all threads: make Mb reusable, then one lane issues the bulk copy
+            if constexpr (RIC) {
+                return;
+            }
             if constexpr (MG) {  // matrix in global memory: a plain cooperative copy H -> working copy
                 gsync<NT>();
                 const int nd2 = (S * (S + 1) / 2) * TS / 2;
@@ -933,6 +956,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
             h_valid = false;
         };
         auto h_need = [&]() {  // all threads: H usable in Mb after this
+            if constexpr (RIC) return;
             if (!h_valid && !h_pending) h_issue();
             if (h_pending) {
                 mbar_wait(&bars[2], hparity);
@@ -970,6 +994,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     BMPC_FOR_ROWS(r, j, k) r_l[r] = mu0 / r_s[r];
                     gsync<NT>();
                 }
+                if constexpr (RIC)
+                    if (attempt >= 0) ric_set_maps<LB, NT>(p, ric, S, nullptr);
                 // ======================= interior-point iterations =========================
                 while (attempt >= 0) {
                     if (it >= p.max_iter) {
@@ -993,7 +1019,9 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         // stationarity residual rd = Hc u + g + C' lam, evaluated once; a Newton step of
                         // length alpha scales it by (1 - alpha) exactly, so afterwards it is carried by
                         // that recurrence (the polish re-derives everything exactly anyway)
-                        tile_symv<LB, NT>(Mb, S, uv, gv, rdv);
+                        if constexpr (RIC) ric_grad<LB, NT>(p, ric, uv, rdv);
+                        else tile_symv<LB, NT>(Mb, S, uv, gv, rdv);
+                        gsync<NT>();
                         double rdp = 0.0;
 #pragma unroll 1
                         for (int i = tid; i < n; i += NT) {
@@ -1011,7 +1039,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     }
                     // M = Hc + blockdiag(Cb' diag(d_j) Cb); predictor rhs = -rd - C'(d rp - lam)
 #pragma unroll 1
-                    for (int e = tid; e < S * NAB; e += NT) {
+                    for (int e = tid; e < (RIC ? 0 : S * NAB); e += NT) {
                         const int j = e / NAB, ab = e - j * NAB;
                         int a = 0, b = ab;  // ab = a(a+1)/2 + b
                         while (b > a) ++a, b -= a;
@@ -1028,11 +1056,20 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     for (int i = tid; i < n; i += NT) xv[i] = -rdv[i] - col_gather(i, r_w);
                     h_valid = false;
                     gsync<NT>();
-                    if (!tile_factor<LB, NT>(Mb, S)) {
+                    bool fact_ok;
+                    if constexpr (RIC) {
+                        RtSpec rt;
+                        rt.polish = 0, rt.Cb = Cb, rt.dd = r_d, rt.mb = mb, rt.Nn = nullptr, rt.bdim = nullptr;
+                        fact_ok = ric_factor<LB, NT>(p, ric, rt);
+                    } else {
+                        fact_ok = tile_factor<LB, NT>(Mb, S);
+                    }
+                    if (!fact_ok) {
                         status = 2;
                         break;
                     }
-                    tile_solve<LB, NT, NPT>(Mb, S, xv);  // xv = du_aff
+                    if constexpr (RIC) ric_solve<LB, NT>(ric, xv);
+                    else tile_solve<LB, NT, NPT>(Mb, S, xv);  // xv = du_aff
                     // affine step: ratio test in FP32 (only a step LENGTH, cut by 0.995 afterwards), and
                     // mu_aff = mu (1 - a) + a^2 sum(dsa dla) / m   because  s dla + lam dsa = -s lam
                     float ratio = 0.f;
@@ -1058,7 +1095,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_c);
                     gsync<NT>();
-                    tile_solve<LB, NT, NPT>(Mb, S, xv);
+                    if constexpr (RIC) ric_solve<LB, NT>(ric, xv);
+                    else tile_solve<LB, NT, NPT>(Mb, S, xv);
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) duv[i] += xv[i];
                     gsync<NT>();
@@ -1092,7 +1130,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
 #pragma unroll 1
                         for (int i = tid; i < n; i += NT) xv[i] = col_gather(i, r_w);
                         gsync<NT>();
-                        tile_solve<LB, NT, NPT>(Mb, S, xv);
+                        if constexpr (RIC) ric_solve<LB, NT>(ric, xv);
+                        else tile_solve<LB, NT, NPT>(Mb, S, xv);
                         h_issue();  // the factor is dead: bring H back while the step length and the update are computed
                         ratio = 0.f;
                         BMPC_FOR_ROWS(r, j, k) {
@@ -1144,13 +1183,15 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                 // guess: row active when its barrier weight lam/s dominates the curvature along it
                 for (int j = tid; j < S; j += NT) amask[j] = 0;
                 h_need();  // diag(Hc) is read from the tile matrix
+                if constexpr (RIC) ric_hdiag<LB, NT>(p, ric, upv);  // ... or evaluated into the (dead) polished-point vector
                 gsync<NT>();
                 BMPC_FOR_ROWS(r, j, k) {
                     const double* cb = Cb + k * LB;
-                    const double* hh = Mb + tidx(j, j) * TS;
+                    const double* hh = RIC ? upv + j * LB : Mb + tidx(j, j) * TS;
+                    constexpr int hstep = RIC ? 1 : LB + 1;
                     double th = 0.0, aa = 0.0;
 #pragma unroll
-                    for (int c = 0; c < LB; ++c) th += cb[c] * cb[c] * hh[c * (LB + 1)], aa += cb[c] * cb[c];
+                    for (int c = 0; c < LB; ++c) th += cb[c] * cb[c] * hh[c * hstep], aa += cb[c] * cb[c];
                     if (r_l[r] * fmax(aa * aa, 1e-300) > th * r_s[r]) atomicOr(&amask[j], 1 << k);
                 }
                 gsync<NT>();
@@ -1169,7 +1210,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     if (gany<NT>(bad_blk)) break;
                     gsync<NT>();
                     h_need();
-                    tile_symv<LB, NT>(Mb, S, ppv, gv, tvp);  // Hc p + g
+                    if constexpr (RIC) ric_grad<LB, NT>(p, ric, ppv, tvp);
+                    else tile_symv<LB, NT>(Mb, S, ppv, gv, tvp);  // Hc p + g
                     gsync<NT>();
                     // reduced system, padded to the tile grid: tile <- N_jr' H N_jc (+ I on the padding)
                     for (int i = tid; i < n; i += NT) {
@@ -1179,7 +1221,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         for (int c = 0; c < LB; ++c) acc += Nn[j * E + c * LB + a] * tvp[j * LB + c];
                         xv[i] = (a < bdim[j]) ? -acc : 0.0;
                     }
-                    {
+                    if constexpr (!RIC) {
                         const int ntile = S * (S + 1) / 2;
                         for (int t = tid; t < ntile; t += NT) {
                             int jr = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
@@ -1219,8 +1261,17 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     }
                     h_valid = false;
                     gsync<NT>();
-                    if (!tile_factor<LB, NT>(Mb, S)) break;
-                    tile_solve<LB, NT, NPT>(Mb, S, xv);
+                    if constexpr (RIC) {
+                        // the same LQR with inputs w_b: B_b N_b in place of B_b, N_b' R N_b (+ I on the padding) as weights
+                        ric_set_maps<LB, NT>(p, ric, S, Nn);
+                        RtSpec rt;
+                        rt.polish = 1, rt.Cb = Cb, rt.dd = nullptr, rt.mb = mb, rt.Nn = Nn, rt.bdim = bdim;
+                        if (!ric_factor<LB, NT>(p, ric, rt)) break;
+                        ric_solve<LB, NT>(ric, xv);
+                    } else {
+                        if (!tile_factor<LB, NT>(Mb, S)) break;
+                        tile_solve<LB, NT, NPT>(Mb, S, xv);
+                    }
                     for (int i = tid; i < n; i += NT) {
                         const int j = i / LB, c = i - j * LB;
                         double acc = ppv[i];
@@ -1245,7 +1296,8 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     }
                     // dual check: minus the gradient must be a non-negative combination of the active rows
                     h_need();
-                    tile_symv<LB, NT>(Mb, S, upv, gv, tvp);
+                    if constexpr (RIC) ric_grad<LB, NT>(p, ric, upv, tvp);
+                    else tile_symv<LB, NT>(Mb, S, upv, gv, tvp);
                     gsync<NT>();
                     int fail = 0;
                     for (int j = tid; j < S; j += NT) {
