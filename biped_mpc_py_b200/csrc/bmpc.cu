@@ -99,6 +99,10 @@ int build_dev_params(const bmpc_params& P, DevParams& d) {
     // polish rounds per attempt: long horizons have more weakly active rows that only show up as violations
     // one round at a time (h = 30 instances needing 5-7 rounds were measured with tools/kernel_model.py)
     d.polish_rounds = P.h > 10 ? 16 : 4;
+    {
+        const char* el = getenv("BMPC_LOCK");  // experiment knob: 3 = lockstep (default), 0 = with an extra step at instance start, 2 = none
+        d.lock_mode = el ? atoi(el) : 3;
+    }
     d.warm_rounds = 6;      // polish rounds allowed to a warm-started tick before it falls back to the cold path
     d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
     memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));

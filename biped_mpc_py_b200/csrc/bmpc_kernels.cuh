@@ -17,7 +17,7 @@ constexpr int IN_DOUBLES = 48;  // x_fb 12 | foot 6 | q 10 | qd 10 | pf_w 6 | pa
 enum RowKind { ROW_LO = 0, ROW_HI = 1, ROW_FRIC = 2, ROW_LINE = 3 };
 
 struct DevParams {
-    int h, extend, LB, mb, npinned, max_iter, gondzio, warm_rounds, polish_rounds;
+    int h, extend, LB, mb, npinned, max_iter, gondzio, warm_rounds, polish_rounds, lock_mode;
     int comps[6];
     int pinned[6];
     int row_kind[MAXROWS];
