@@ -53,6 +53,7 @@ struct bmpc_handle {
     bmpc_params host_params;
     DevParams dp;
     Variant bucket[2];
+    Variant lowlat;           // walking class for small batches: 128 threads per robot (latency, not throughput), or empty
     Variant fallback;         // dense re-solve of instances the stage-wise class-1 kernel did not certify (h = 30), or empty
     int* d_lists = nullptr;   // [3][max_batch]: two classes + the fallback list
     int* d_counts = nullptr;  // [3]
@@ -195,7 +196,10 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
     for (int b = 0; b < 2; ++b) {
-        const Variant& v = h->bucket[b];
+        // real-time use (N = 1 .. 8): every walking robot gets a whole 128-thread CTA (0.26 ms instead of 0.32 ms for one
+        // robot end to end).  Same optimum, but reductions run in a different order, so results of batches <= 8 may
+        // differ in the last bits from the throughput kernel; every larger batch is bit-identical under any split.
+        const Variant& v = (b == 0 && h->lowlat.fn && n <= 8) ? h->lowlat : h->bucket[b];
         // persistent thread groups: as many as fit on the device, each strides over its bucket's work list
         const int grid = (std::min(n, v.resident) + v.per_cta - 1) / v.per_cta;
         v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b,
@@ -274,6 +278,8 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
                          : setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)) ||
              (nts == 256 ? setup_variant<10, 20, 5, 256, 1>(h->bucket[1], h->num_sms, h->dp.mb)
                          : setup_variant<10, 20, 5, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb));
+        const char* ell = getenv("BMPC_LOWLAT");
+        if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, h->num_sms, h->dp.mb);
     } else {
         rc = setup_variant<10, 10, 6, 32, 4>(h->bucket[0], h->num_sms, h->dp.mb) ||
              setup_variant<10, 20, 6, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb);
@@ -300,6 +306,7 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaFree(h->d_counts);
     for (int b = 0; b < 2; ++b) cudaFree(h->bucket[b].d_scratch);
     cudaFree(h->fallback.d_scratch);
+    cudaFree(h->lowlat.d_scratch);
     cudaFree(h->ro.contact), cudaFree(h->ro.phase_k), cudaFree(h->ro.t_swing), cudaFree(h->ro.controls);
     cudaFree(h->ro.tau), cudaFree(h->ro.status), cudaFree(h->ro.iters), cudaFree(h->ro.ws_mask);
     for (int i = 0; i < 4; ++i)
