@@ -263,15 +263,21 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         // instances it does not certify.  BMPC_H30=dense / ric force one backend for both classes (experiments).
         const char* er = getenv("BMPC_H30");
         const std::string mode = er ? er : "hybrid";
+        const char* en = getenv("BMPC_RIC_NT");
+        const int rnt = en ? atoi(en) : 128;
         if (mode == "dense")
             rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
                  setup_variant<30, 60, 5, 256, 1, true>(h->bucket[1], h->num_sms, h->dp.mb);
         else if (mode == "ric")
-            rc = setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], h->num_sms, h->dp.mb) ||
-                 setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb);
+            rc = (rnt == 32 ? (setup_variant<30, 30, 5, 32, 1, false, true>(h->bucket[0], h->num_sms, h->dp.mb) ||
+                               setup_variant<30, 60, 5, 32, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb))
+                            : (setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], h->num_sms, h->dp.mb) ||
+                               setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb))) ||
+                 setup_variant<30, 60, 5, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
         else
             rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
-                 setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb) ||
+                 (rnt == 32 ? setup_variant<30, 60, 5, 32, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb)
+                            : setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb)) ||
                  setup_variant<30, 60, 5, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
     } else if (h->dp.LB == 5) {
         rc = (nww == 1 ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)

@@ -333,7 +333,7 @@ struct TickLayout {
     static constexpr int NAB = LB * (LB + 1) / 2;
     // ---- shared memory ----
     static constexpr int o_M = 0;
-    static constexpr int RB = (Ric<LB>::doubles(HZ, SMAX) + 1) & ~1;
+    static constexpr int RB = (Ric<LB, HZ, SMAX>::total + 1) & ~1;
     static constexpr int o_in = o_M + (RIC ? RB : (MG ? 0 : MB));   // 2 x IN_DOUBLES TMA destinations (inputs, double buffered)
     static constexpr int o_g = o_in + 2 * IN_DOUBLES;
     static constexpr int o_u = o_g + NV;
@@ -438,12 +438,10 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
     int* misc = bdim + SMAX;          // [0]=S  [1]=flag
     int* sfirst = misc + 16;          // [HZ] first block of each stage (Riccati backend)
     int* scnt = sfirst + HZ;          // [HZ] blocks per stage
-    Ric<LB> ric;
-    if constexpr (RIC) {
-        ric.carve(sm + L::o_M, HZ, SMAX);
-        ric.sfirst = sfirst, ric.scnt = scnt, ric.blk_foot = blk_foot;
-        ric.dt = p.dt, ric.vm = p.dt / p.mass;
-    }
+    Ric<LB, HZ, SMAX> ric;  // stage-wise backend: one base pointer + compile-time offsets, passed by value
+    ric.b = sm + L::o_M;
+    ric.sfirst = sfirst, ric.scnt = scnt, ric.blk_foot = blk_foot;
+    ric.dt = p.dt, ric.vm = p.dt / p.mass;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::o_bar);  // [0],[1] inputs, [2] H reload
 
     const int count = *work_count;
@@ -879,9 +877,9 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
         }
         gsync<NT>();
         if constexpr (RIC) {  // problem data the stage-wise backend keeps for the whole solve
-            for (int i = tid; i < S * 3 * LB; i += NT) ric.W0[i] = Wm[i];
-            for (int i = tid; i < HZ * 9; i += NT) ric.rinv[i] = rinv[i];
-            for (int i = tid; i < HZ * 12; i += NT) ric.err[i] = err[i];
+            for (int i = tid; i < S * 3 * LB; i += NT) ric.W0()[i] = Wm[i];
+            for (int i = tid; i < HZ * 9; i += NT) ric.rinv()[i] = rinv[i];
+            for (int i = tid; i < HZ * 12; i += NT) ric.err()[i] = err[i];
         }
         // the assembly arrays are needed again only by the output stage: park them in the scratch
         for (int i = tid; i < L::a_end - L::o_work; i += NT) gsave[i] = sm[L::o_work + i];
@@ -1064,7 +1062,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     if constexpr (RIC) {
                         RtSpec rt;
                         rt.polish = 0, rt.Cb = Cb, rt.dd = r_d, rt.mb = mb, rt.Nn = nullptr, rt.bdim = nullptr;
-                        fact_ok = ric_factor<LB, NT>(p, ric, rt);
+                        fact_ok = ric_factor<LB, NT>(p, ric, rt, S);
                     } else {
                         fact_ok = tile_factor<LB, NT>(Mb, S);
                     }
@@ -1270,7 +1268,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         ric_set_maps<LB, NT>(p, ric, S, Nn);
                         RtSpec rt;
                         rt.polish = 1, rt.Cb = Cb, rt.dd = nullptr, rt.mb = mb, rt.Nn = Nn, rt.bdim = bdim;
-                        if (!ric_factor<LB, NT>(p, ric, rt)) break;
+                        if (!ric_factor<LB, NT>(p, ric, rt, S)) break;
                         ric_solve<LB, NT>(ric, xv);
                     } else {
                         if (!tile_factor<LB, NT>(Mb, S)) break;
