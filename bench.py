@@ -45,15 +45,17 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="instances per GPU per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch instances per GPU (default); strong: --batch instances in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short h=30 and closed-loop rollout legs")
     return ap.parse_args()
 
 
-def workload_config(batch, n_gpus):
+def workload_config(batch, n_gpus, scaling="weak"):
     return {"workload": f"{batch} independent horizon-10 biped MPC ticks per GPU per step (BASELINE.json configs[2], "
-                        f"weak scaling; 85% walking / 15% standing, SURVEY.md 8d distribution)",
+                        f"{scaling} scaling; 85% walking / 15% standing, SURVEY.md 8d distribution)",
             "instances_per_gpu": batch, "horizon": 10, "parallelism": f"shard{n_gpus} (independent instances, no hot-path collective)",
             "l2_policy": "per-step inputs+outputs (~0.37 GB per GPU at 262144) exceed the 126 MB L2"}
 
@@ -264,6 +266,10 @@ def run_b200(args, rank, local_rank, world):
 
     mpc, biped = MPC(), Biped()
     n = args.batch
+    if args.scaling == "strong":  # fixed total work: contiguous shard of the same global batch
+        from biped_mpc_py_b200.shard import shard_slice
+        sl = shard_slice(args.batch, rank, world)
+        n = sl.stop - sl.start
     batch = synth.make_batch(n, shard_index=rank, mpc=mpc, biped=biped)
     solver = BatchedMPC(mpc, biped, max_batch=n, device=local_rank)
     tn = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
@@ -291,7 +297,8 @@ def run_b200(args, rank, local_rank, world):
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     ms_per_step = ms_total / args.steps
-    value = world * n / (ms_per_step * 1e-3)
+    total_n = int(sum_over_ranks(float(n)))
+    value = total_n / (ms_per_step * 1e-3)
 
     iters = out["iters"].cpu().numpy()
     status = out["status"].cpu().numpy()
@@ -314,19 +321,26 @@ def run_b200(args, rank, local_rank, world):
         kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
                         "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"]})
     dom = int(np.argmax(kt[1:]))
-    traffic = None
+    traffic, secondary = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from one ncu capture of this batch size
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if int(tj.get("batch", -1)) == n:
             traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
+        kd = tj["kernels"][dom]
+        if "smem_wavefronts_pct_of_peak" in kd:  # the nearest hardware limit per ncu (not measured live: profiler-only counters)
+            secondary = {"what": "pipe utilisation of the dominant kernel from the committed ncu capture",
+                         "smem_wavefronts_pct_of_peak": kd["smem_wavefronts_pct_of_peak"],
+                         "fp64_pipe_pct_busy": kd["fp64_pipe_pct_busy"], "issue_slots_pct_busy": kd["issue_slots_pct_busy"],
+                         "source": tj.get("pipe_source")}
     roofline = {"bound": "fp64_fma", "achieved": kernels[dom]["achieved_tflops"], "peak": peaks["fp64_fma_tflops"],
                 "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": traffic,
                 "peak_source": "measured in this run by bmpc_measure_fma_peak (register-resident DFMA chains on all SMs); "
                                "MEASURED_PEAKS.json carries no FP64 CUDA-core figure",
                 "fp32_fma_peak_tflops": peaks["fp32_fma_tflops"], "dominant_kernel": kernels[dom]["kernel"],
                 "kernels": kernels, "classify_ms": float(kt[0]),
-                "share_of_step": {"walking": float(kt[1] / kt.sum()), "standing": float(kt[2] / kt.sum())}}
+                "share_of_step": {"walking": float(kt[1] / kt.sum()), "standing": float(kt[2] / kt.sum())},
+                "secondary": secondary}
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------
     tick = solver.pinned_tick(n, lowlevel=True, want_states=False)
@@ -341,7 +355,7 @@ def run_b200(args, rank, local_rank, world):
         _ = float(res["tau"][0, 0])  # host read of the step's result
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": world * n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tick.h2d_bytes),
+    e2e = {"value": total_n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tick.h2d_bytes),
            "d2h_bytes_per_step": int(tick.d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
            "api": "BatchedMPC.pinned_tick(n).run(): pinned host -> device, bmpc_step, device -> pinned host, sync"}
 
@@ -375,8 +389,8 @@ def run_b200(args, rank, local_rank, world):
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_leg(per_core=12)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world, args.scaling),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "latency": latency, "other_configs": extra,
                 "solver": {"mean_iters": float(stats["mean_iters"]), "max_iters": int(stats["iters_max"]),
