@@ -315,7 +315,7 @@ def run_b200(args, rank, local_rank, world):
     fl = batch_flops(batch["contact"], iters)
     peaks = measure(local_rank)
     kernels = []
-    for cls, name in ((0, "mpc_tick2_kernel<10,10,5,32,5> (<=10 stance foot-stages: walking class, one warp per robot, 5 robots per CTA)"),
+    for cls, name in ((0, "mpc_tick2_kernel<10,10,5,32,8> (<=10 stance foot-stages: walking class, one warp per robot, 8 robots per CTA)"),
                       (1, "mpc_tick2_kernel<10,20,5,128,1> (11..20 stance foot-stages: standing class, one CTA per robot)")):
         ach = fl[cls] / (kt[1 + cls] * 1e-3) / 1e12 if kt[1 + cls] > 0 else 0.0
         kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
@@ -332,6 +332,7 @@ def run_b200(args, rank, local_rank, world):
             secondary = {"what": "pipe utilisation of the dominant kernel from the committed ncu capture",
                          "smem_wavefronts_pct_of_peak": kd["smem_wavefronts_pct_of_peak"],
                          "fp64_pipe_pct_busy": kd["fp64_pipe_pct_busy"], "issue_slots_pct_busy": kd["issue_slots_pct_busy"],
+                         "gcc_instruction_cache_busy_pct": kd.get("gcc_instruction_cache_busy_pct"),
                          "source": tj.get("pipe_source")}
     roofline = {"bound": "fp64_fma", "achieved": kernels[dom]["achieved_tflops"], "peak": peaks["fp64_fma_tflops"],
                 "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": traffic,

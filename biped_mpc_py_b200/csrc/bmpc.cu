@@ -173,6 +173,7 @@ int setup_variant(Variant& v, int num_sms, int mb) {
     using L = TickLayout<HZ, SMAX, LB, MG, RIC>;
     v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT, NW, MG, RIC>;
     v.smem = L::bytes(mb) * NW + 16;  // + the CTA-wide lockstep mbarrier
+    if (const char* ep = getenv("BMPC_PAD_SMEM")) v.smem += (size_t)atoi(ep);  // occupancy experiments only
     v.threads = NT * NW;
     v.per_cta = NW;
     v.scratch_doubles = L::g_total;
@@ -250,7 +251,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
     // experiment knobs (threads per robot in each class); the defaults are the shipped configuration
     const char* ew = getenv("BMPC_NW_WALK");
     const char* es = getenv("BMPC_NT_STAND");
-    const int nww = ew ? atoi(ew) : 5, nts = es ? atoi(es) : 128;  // walking: robots per CTA; standing: threads per robot
+    const int nww = ew ? atoi(ew) : 8, nts = es ? atoi(es) : 128;  // walking: robots per CTA; standing: threads per robot
     if (h->dp.h == 30) {
         // h = 30 (BASELINE.json configs[3]): walking class S <= 30 with the tile matrix in shared memory
         // (97 KB, one CTA per SM), standing class S <= 60 with it in the L2-resident scratch (380 KB)
@@ -280,14 +281,15 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
                             : setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb)) ||
                  setup_variant<30, 60, 5, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
     } else if (h->dp.LB == 5) {
-        rc = (nww == 1 ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
-                         : setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)) ||
+        rc = (nww == 1   ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
+              : nww == 5 ? setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)
+                         : setup_variant<10, 10, 5, 32, 8>(h->bucket[0], h->num_sms, h->dp.mb)) ||
              (nts == 256 ? setup_variant<10, 20, 5, 256, 1>(h->bucket[1], h->num_sms, h->dp.mb)
                          : setup_variant<10, 20, 5, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb));
         const char* ell = getenv("BMPC_LOWLAT");
         if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, h->num_sms, h->dp.mb);
     } else {
-        rc = setup_variant<10, 10, 6, 32, 4>(h->bucket[0], h->num_sms, h->dp.mb) ||
+        rc = setup_variant<10, 10, 6, 32, 6>(h->bucket[0], h->num_sms, h->dp.mb) ||
              setup_variant<10, 20, 6, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb);
     }
     if (rc) {
