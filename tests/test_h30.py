@@ -58,3 +58,29 @@ def test_h30_batch_all_certified_and_split_invariant():
     np.testing.assert_array_equal(half["controls"], full["controls"][:n // 2])
     np.testing.assert_array_equal(half["tau"], full["tau"][:n // 2])
     s.close()
+
+
+def test_h30_mixed_contact_patterns_against_oracle():
+    """Arbitrary schedules at h = 30 (flight stages, single and double support in any order): both classes - the dense
+    walking-class kernel (<= 30 stance foot-stages) and the stage-wise standing-class kernel (stages with 0, 1, 2 feet)."""
+    from oracle import reference_mpc as rm
+    from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
+    mpc_o, biped_o = rm.MPCParams(h=30), rm.BipedParams()
+    mpc = MPC(h=30)
+    n = 12
+    b = synth.make_batch(n, shard_index=14, mpc=mpc, extend=True)
+    rng = np.random.default_rng(14)
+    dens = np.where(np.arange(n) % 2 == 0, 0.4, 0.8)          # half below, half above 30 stance foot-stages
+    b["contact"] = (rng.uniform(size=(n, 30, 2)) < dens[:, None, None]).astype(np.uint8)
+    S = b["contact"].reshape(n, -1).sum(axis=1)
+    assert (S <= 30).any() and (S > 30).any()
+    s = BatchedMPC(mpc, Biped(), max_batch=n, extend_gait=True)
+    out = s.step_host(b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"], phase_k=b["phase_k"])
+    assert (out["status"] == 0).all(), (out["status"], S)
+    for i in range(n):
+        st, ct = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc_o, biped_o, b["contact"][i], extend=True)
+        tau = rm.lowLevelControl(b["x_fb"][i], float(b["t"][i]), b["pf_w"][i].reshape(6, 1), b["q"][i], b["qd"][i], mpc_o,
+                                 biped_o, b["contact"][i], ct[0].reshape(-1, 1)).reshape(-1)
+        assert np.abs(out["controls"][i] - ct).max() / max(1.0, np.abs(ct).max()) <= U_RTOL, (i, S[i])
+        assert np.abs(out["tau"][i] - tau).max() <= TAU_ATOL, (i, S[i])
+    s.close()
