@@ -22,7 +22,7 @@ struct DevParams {
     int pinned[6];
     int row_kind[MAXROWS];
     int row_arg[MAXROWS];
-    double dt, kv, swing_height, mass, lt_eff, lh_eff, g, mu, mu_tol, rd_tol, init_fz_frac, mu0_scale, step_frac;
+    double dt, kv, swing_height, mass, lt_eff, lh_eff, g, mu, mu_tol, rd_tol, init_fz_frac, mu0_scale, step_frac, gondzio_below;
     double x_cmd[12], Q[13], R[12], kp[9], kd[9], inertia[9], hip[3], lo6[6], hi6[6];
 };
 

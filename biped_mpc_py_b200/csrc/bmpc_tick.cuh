@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                     // Gondzio centrality corrector: pull outlier products of the trial point into
                     // [0.1, 10] x target; one more pair of triangular solves with the same factor.
                     // Direction change: du += x, ds -= C x, dlam += d (C x) - w,  w = -vt / s
-                    if (p.gondzio) {
+                    if (p.gondzio && a2 < p.gondzio_below) {
                         const double at = fmin(1.0, 1.5 * a2 + 0.1);
                         BMPC_FOR_ROWS(r, j, k) {
                             const double v = (r_s[r] + at * r_p[r]) * (r_l[r] + at * r_c[r]);
@@ -1163,7 +1163,7 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
 #pragma unroll 1
                     for (int i = tid; i < n; i += NT) uv[i] += alpha * duv[i], rdv[i] *= (1.0 - alpha);
                     rdmax *= (1.0 - alpha);
-                    if (!p.gondzio) h_issue();
+                    if (!h_pending && !h_valid) h_issue();  // (the Gondzio branch issues it earlier when it runs)
                     gsync<NT>();
                 }
 
