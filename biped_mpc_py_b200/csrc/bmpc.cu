@@ -196,7 +196,7 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
                  (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
-    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 3 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 6 * sizeof(int), st));  // three list counts + three dynamic work counters
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
@@ -301,7 +301,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         return 1;
     }
     e = cudaMalloc(&h->d_lists, sizeof(int) * 3 * (size_t)max_batch);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 6);
     if (e != cudaSuccess) {
         cudaFree(h->d_lists);
         delete h;
