@@ -386,6 +386,35 @@ def run_b200(args, rank, local_rank, world):
             latency = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "samples": len(lat),
                        "what": "N=1 tick, pinned host in -> tau/controls on host, includes launch + copies + sync"}
             one.close()
+            # the same call inside a caller-owned control loop for one walking robot (states replayed from a device rollout):
+            # cold ticks vs ticks warm-started from the previous tick's certified active set (bmpc_warm_start)
+            rb = synth.make_rollout_batch(64, shard_index=4)
+            i = int(np.nonzero(rb["gait"] == 1)[0][0])
+            loop = BatchedMPC(mpc, synth.rollout_biped(), max_batch=1, device=local_rank)
+            nt = 160
+            stt = [tn(rb[k][i:i + 1], dt) for k, dt in (("x", torch.float64), ("foot", torch.float64), ("tick", torch.int32),
+                                                         ("gait", torch.uint8), ("q", torch.float64), ("qd", torch.float64))]
+            lg = loop.rollout(*stt, nt, warm_start=False, n_log=1)
+            torch.cuda.synchronize(dev)
+            xl, fl = lg["x_log"].cpu().numpy()[:, 0], lg["foot_log"].cpu().numpy()[:, 0]
+            tl = loop.pinned_tick(1)
+            for warm in (False, True):
+                loop.warm_start(warm)
+                ll = []
+                for k in range(nt):
+                    T = int(rb["tick"][i]) + k
+                    rows = (T + np.arange(10)) % 10
+                    tl.inputs["x_fb"][0], tl.inputs["foot"][0], tl.inputs["pf_w"][0] = xl[k], fl[k], fl[k]
+                    tl.inputs["q"][0], tl.inputs["qd"][0], tl.inputs["t"][0] = rb["q"][i], rb["qd"][i], T * mpc.dt
+                    tl.inputs["phase_k"][0] = T % 10
+                    tl.inputs["contact"][0] = np.stack([rows < 5, rows >= 5], axis=1).astype(np.uint8)
+                    a = time.perf_counter()
+                    tl.run()
+                    ll.append(time.perf_counter() - a)
+                latency["loop_warm_p50_ms" if warm else "loop_cold_p50_ms"] = float(np.percentile(np.array(ll[20:]) * 1e3, 50))
+            latency["loop_what"] = ("one walking robot in a caller-owned control loop (160 ticks, states from a device rollout): "
+                                    "cold ticks vs bmpc_warm_start ticks; same certified optimum")
+            loop.close()
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_leg(per_core=12)

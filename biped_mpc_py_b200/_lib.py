@@ -9,7 +9,7 @@ from .params import BmpcParams
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbiped_mpc_b200.so")
 
-EXPORTS = ["bmpc_create", "bmpc_destroy", "bmpc_step", "bmpc_solve", "bmpc_lowlevel", "bmpc_foot_positions", "bmpc_rollout",
+EXPORTS = ["bmpc_create", "bmpc_destroy", "bmpc_step", "bmpc_solve", "bmpc_lowlevel", "bmpc_foot_positions", "bmpc_rollout", "bmpc_warm_start",
            "bmpc_debug_assemble", "bmpc_launch_count", "bmpc_enable_timing", "bmpc_last_timing", "bmpc_measure_fma_peak", "bmpc_last_error",
            "bmpc_abi_version"]
 
@@ -46,6 +46,8 @@ def load():
     lib.bmpc_foot_positions.restype = c_int
     lib.bmpc_rollout.argtypes = [c_void_p, c_int, c_int] + [vp] * 6 + [c_int, c_int] + [vp] * 5 + [vp]
     lib.bmpc_rollout.restype = c_int
+    lib.bmpc_warm_start.argtypes = [c_void_p, c_int]
+    lib.bmpc_warm_start.restype = c_int
     lib.bmpc_debug_assemble.argtypes = [c_void_p] + [vp] * 7 + [vp]
     lib.bmpc_debug_assemble.restype = c_int
     lib.bmpc_launch_count.argtypes = [c_void_p]

@@ -69,6 +69,8 @@ struct bmpc_handle {
         int32_t* iters = nullptr;
         int32_t* ws_mask = nullptr;
     } ro;
+    int warm_enabled = 0;        // bmpc_warm_start: bmpc_step / bmpc_solve start from the previous call's active set
+    int warm_valid = 0;          // the store holds the masks of a previous call
     int timing = 0;              // record CUDA events around each kernel of a tick
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -194,6 +196,12 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n > h->max_batch) return fail("batch larger than max_batch given to bmpc_create");
     auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (h->warm_enabled && io.ws_mask == nullptr) {  // handle-level warm start (bmpc_warm_start); bmpc_rollout manages its own
+        if (!h->ro.ws_mask) CUDA_TRY(cudaMalloc(&h->ro.ws_mask, (size_t)h->max_batch * h->dp.h * 2 * sizeof(int32_t)));
+        io.ws_mask = h->ro.ws_mask;
+        io.warm = h->warm_valid;
+        h->warm_valid = 1;
+    }
     io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
                  (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
     CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 6 * sizeof(int), st));  // three list counts + three dynamic work counters
@@ -404,6 +412,8 @@ int bmpc_rollout(bmpc_handle* h, int n, int ticks, double* x, double* foot, int3
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int hz = h->dp.h;
     const size_t nb = (size_t)h->max_batch;
+    h->warm_valid = 0;  // the rollout shares the warm-start store: a later warm bmpc_step starts cold
+    if (!h->ro.ws_mask) CUDA_TRY(cudaMalloc(&h->ro.ws_mask, nb * hz * 2 * sizeof(int32_t)));
     if (!h->ro.contact) {
         CUDA_TRY(cudaMalloc(&h->ro.contact, nb * hz * 2));
         CUDA_TRY(cudaMalloc(&h->ro.phase_k, nb * sizeof(int32_t)));
@@ -412,7 +422,6 @@ int bmpc_rollout(bmpc_handle* h, int n, int ticks, double* x, double* foot, int3
         CUDA_TRY(cudaMalloc(&h->ro.tau, nb * 10 * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->ro.status, nb * sizeof(int32_t)));
         CUDA_TRY(cudaMalloc(&h->ro.iters, nb * sizeof(int32_t)));
-        CUDA_TRY(cudaMalloc(&h->ro.ws_mask, nb * hz * 2 * sizeof(int32_t)));
     }
     RolloutPtrs r;
     memset(&r, 0, sizeof(r));
@@ -429,14 +438,32 @@ int bmpc_rollout(bmpc_handle* h, int n, int ticks, double* x, double* foot, int3
     io.do_lowlevel = 1;
     io.ws_mask = warm_start ? h->ro.ws_mask : nullptr;
     const int threads = 128, blocks = (n + threads - 1) / threads;
+    const int saved_warm = h->warm_enabled;
+    h->warm_enabled = 0;  // the rollout passes its own warm-start store (or none) to the tick
     for (int k = 0; k < ticks; ++k) {
         rollout_prepare_kernel<<<blocks, threads, 0, st>>>(h->dp, r, n, k);
         io.warm = (warm_start && k > 0) ? 1 : 0;  // the first tick of a call is always cold
-        if (launch_tick(h, n, io, st)) return 1;
+        if (launch_tick(h, n, io, st)) {
+            h->warm_enabled = saved_warm;
+            return 1;
+        }
         rollout_advance_kernel<<<blocks, threads, 0, st>>>(h->dp, r, n, k);
         h->launches += 2;
     }
+    h->warm_enabled = saved_warm;
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bmpc_warm_start(bmpc_handle* h, int mode) {
+    if (!h) return fail("bmpc_warm_start: null handle");
+    if (mode < 0 || mode > 2) return fail("bmpc_warm_start: mode must be 0 (off), 1 (on) or 2 (forget the stored active sets)");
+    if (mode == 2) {
+        h->warm_valid = 0;
+        return 0;
+    }
+    h->warm_enabled = mode;
+    h->warm_valid = 0;
     return 0;
 }
 
@@ -457,7 +484,10 @@ int bmpc_debug_assemble(bmpc_handle* h, const double* x_fb, const int32_t* phase
     io.status = reinterpret_cast<int32_t*>(scratch + hz * 12);
     io.iters = io.status + 1;
     io.dbg_H = Hc_out, io.dbg_g = g_out, io.dbg_n = n_out;
+    const int saved_warm = h->warm_enabled;
+    h->warm_enabled = 0;
     int rc = launch_tick(h, 1, io, st);
+    h->warm_enabled = saved_warm;
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(scratch);
     if (rc) return rc;

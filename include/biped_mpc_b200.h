@@ -123,6 +123,14 @@ int bmpc_rollout(bmpc_handle* h, int n, int ticks,
                  int n_log, double* x_log, double* foot_log, double* u0_log, double* tau_log,
                  uint64_t* stats, void* stream);
 
+/* Warm start across calls for a caller-owned control loop (the reference solves cold every
+ * call, MPC.py:297).  mode 1: every following bmpc_step / bmpc_solve assumes that robot i of the batch is the same
+ * robot ONE control tick later (horizon shifted by one stage) and starts from the active set certified by the
+ * previous call (first call: cold).  A guess that does not certify falls back to the cold solve, so results are the
+ * same certified optimum either way.  mode 0: off (default).  mode 2: forget the stored sets (after a reset / a
+ * jump in time), stay on. */
+int bmpc_warm_start(bmpc_handle* h, int mode);
+
 /* Debug / parity: the contact-reduced condensed QP of instance `index` of the last
  * bmpc_step/bmpc_solve inputs.  Hc_out[nmax*nmax] row-major (nmax = 12*h), g_out[nmax],
  * n_out = number of reduced variables, all DEVICE pointers.  Synchronous. */

@@ -192,3 +192,40 @@ def test_rollout_long_horizon_stays_certified():
     assert np.isfinite(res["final_x"]).all()
     assert np.abs(res["final_x"][:, 0:3]).max() <= 0.8 and np.abs(res["final_x"][:, 5] - 0.55).max() < 0.3
     assert sn["falls"] < 0.001 * n * ticks / 100, sn  # R7 resets are rare (about 1 robot in 4,000 per 300 ticks)
+
+
+@pytest.mark.gpu
+def test_handle_warm_start_in_a_caller_owned_loop():
+    """``bmpc_warm_start``: a loop the CALLER owns (one ``step`` per tick, states fed back by the caller - here the logged
+    states of a device rollout) gives the same results warm and cold, and the warm ticks skip the interior point."""
+    import torch
+    from biped_mpc_py_b200 import BatchedMPC, MPC, synth
+    n, ticks = 64, 12
+    b, res = _gpu_rollout(n, ticks, False, n_log=n, shard=6)
+    s = BatchedMPC(MPC(), synth.rollout_biped(), max_batch=n)
+    dev = s.device
+    tn = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    q, qd = tn(b["q"]), tn(b["qd"])
+    outs = {}
+    for warm in (False, True):
+        s.warm_start(warm)
+        u0, iters = [], []
+        for k in range(ticks):
+            tick = b["tick"] + k
+            phase = tn((tick % 10).astype(np.int32), torch.int32)
+            walking = b["gait"][:, None, None] == 1
+            rows = (tick[:, None] + np.arange(10)[None, :]) % 10
+            contact = np.where(walking, np.stack([rows < 5, rows >= 5], axis=2), True).astype(np.uint8)
+            x, foot = tn(res["x_log"][k]), tn(res["foot_log"][k])
+            out = s.step(x, phase, tn(tick * 0.04), foot, tn(contact, torch.uint8), q, qd, foot)
+            torch.cuda.synchronize()
+            assert (out["status"].cpu().numpy() == 0).all()
+            u0.append(out["controls"][:, 0, :].cpu().numpy().copy())
+            iters.append(out["iters"].cpu().numpy().copy())
+        outs[warm] = (np.array(u0), np.array(iters))
+    np.testing.assert_allclose(outs[True][0], outs[False][0], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(outs[False][0], res["u0_log"], rtol=1e-9, atol=1e-9)   # the caller's loop == bmpc_rollout
+    assert outs[True][1][0].min() > 0                      # first warm call is cold
+    assert (outs[True][1][1:] == 0).mean() > 0.9           # later ticks: straight to the polish
+    s.reset_warm_start()
+    s.close()
