@@ -297,6 +297,27 @@ class BatchedMPC:
         self.last_h2d_bytes, self.last_d2h_bytes = tick.h2d_bytes, tick.d2h_bytes
         return {k: v.copy() for k, v in out.items()}
 
+    def tick_host(self, x_fb, t, q, qd, gait, want_states: bool = False):
+        """One control tick for N robots in the reference script's call order (MPC.py:475-495): forward kinematics
+        ``pf_w = getFootPositionWorld(x_fb, q)`` and ``foot = pf_w`` (MPC.py:478-479), the contact schedule from ``t`` and
+        ``gait`` (1 walking: ``get_contact_sequence``, 0 standing: ones; MPC.py:481-484), ``solve_mpc`` and
+        ``lowLevelControl`` on ``controls[0]`` (MPC.py:487-494).  Host numpy in / out; FK, solve and torque map run on the
+        device, the gait table and the float phase (MPC.py:56) on the host.  Returns the ``step_host`` dict plus ``pf_w``
+        and ``contact``."""
+        torch = _torch()
+        from .gait import batch_contact_and_phase
+        x_fb = np.ascontiguousarray(x_fb, dtype=np.float64).reshape(-1, 12)
+        n = x_fb.shape[0]
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(n, 10)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(n)
+        gait = np.broadcast_to(np.asarray(gait), (n,))
+        dev = self.device
+        pf_w = self.foot_positions(torch.as_tensor(x_fb, device=dev), torch.as_tensor(q, device=dev)).cpu().numpy()
+        contact, phase_k = batch_contact_and_phase(t, gait, self.mpc, extend=self.extend_gait)
+        out = self.step_host(x_fb, t, pf_w, contact, q, qd, pf_w, phase_k=phase_k, want_states=want_states)
+        out["pf_w"], out["contact"] = pf_w, contact
+        return out
+
     def solve_host(self, x_fb, t, foot, contact, phase_k=None, want_states: bool = True):
         """``solve_mpc`` only, host numpy in / out."""
         return self.step_host(x_fb, t, foot, contact, None, None, None, phase_k=phase_k, want_states=want_states,
@@ -413,3 +434,16 @@ def getFootPositionWorld(x_fb, q, biped, mpc=None):
     tn = lambda a, shape: torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(shape), dtype=torch.float64,
                                           device=s.device)
     return s.foot_positions(tn(x_fb, (1, 12)), tn(q, (1, 10)))[0].cpu().numpy().reshape(6, 1)
+
+
+def mpc_tick(x_fb, t, q, qd, mpc, biped, gait: int = 1):
+    """The reference's main script as a function (MPC.py:475-495), one robot: FK, contact schedule, ``solve_mpc``,
+    ``lowLevelControl``.  Returns dict(states (h,13), controls (h,12), tau (10,1), pf_w (6,1), contact (h,2)).
+    For a control loop call ``default_solver(mpc, biped).warm_start(True)`` once before the first tick."""
+    s = default_solver(mpc, biped)
+    out = s.tick_host(np.asarray(x_fb, dtype=np.float64).reshape(1, 12), np.array([float(t)]), np.asarray(q).reshape(1, 10),
+                      np.asarray(qd).reshape(1, 10), np.array([int(gait)]), want_states=True)
+    if int(out["status"][0]) == STATUS_BADINPUT:
+        raise ValueError("mpc_tick: non-finite input or singular euler-rate matrix (pitch = +-pi/2)")
+    return dict(states=out["states"][0], controls=out["controls"][0], tau=out["tau"][0].reshape(10, 1),
+                pf_w=out["pf_w"][0].reshape(6, 1), contact=out["contact"][0])

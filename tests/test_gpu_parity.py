@@ -217,6 +217,33 @@ def test_reference_signatures_known_answers(torch_cuda):
         assert (qp["G"] @ z - qp["hv"]).max() < 1e-9               # feasible
 
 
+def test_reference_script_tick_known_answers_and_batch(torch_cuda):
+    """``mpc_tick`` = the reference's main script (MPC.py:475-495) as a function: FK -> contact -> solve -> torques.
+    G1-G4 from the file's initial state, and a batch of random joint states against the oracle's ``mpc_tick``."""
+    import biped_mpc_py_b200 as bm
+    from test_oracle_golden import G_CASES
+    from oracle import reference_mpc as rm
+    mpc, biped = bm.MPC(), bm.Biped()
+    for name, case in G_CASES.items():
+        out = bm.mpc_tick(rm.X_FB0, case["t"], rm.Q0, rm.QD0, mpc, biped, gait=case["gait"])
+        np.testing.assert_allclose(out["controls"][0], case["u0"], rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(out["tau"].reshape(-1), case["tau"], rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(out["pf_w"].reshape(-1), [-0.02, 0.09, -0.003126983722081, -0.02, -0.09, -0.003126983722081],
+                                   atol=1e-13)
+        assert out["states"].shape == (10, 13) and out["contact"].shape == (10, 2)
+    solver, mpc_o, biped_o = _solver(0, max_batch=16)
+    b = bm.synth.make_batch(16, shard_index=8)
+    out = solver.tick_host(b["x_fb"], b["t"], b["q"], b["qd"], b["gait"])
+    np.testing.assert_allclose(out["pf_w"], b["pf_w"], atol=1e-13)
+    np.testing.assert_array_equal(out["contact"], b["contact"])
+    for i in range(16):
+        ref = rm.mpc_tick(b["x_fb"][i], float(b["t"][i]), b["q"][i], b["qd"][i], mpc_o, biped_o, gait=int(b["gait"][i]))
+        scale = max(1.0, np.abs(ref["controls"]).max())
+        assert np.abs(out["controls"][i] - ref["controls"]).max() / scale <= U_RTOL_TIGHT
+        assert np.abs(out["tau"][i] - ref["tau"].reshape(-1)).max() <= TAU_ATOL_TIGHT
+    solver.close()
+
+
 def test_bad_inputs_are_flagged_not_solved(torch_cuda):
     from biped_mpc_py_b200 import synth
     solver, mpc, biped = _solver(0, max_batch=8)
