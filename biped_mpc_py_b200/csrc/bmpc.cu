@@ -267,13 +267,11 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
     if (h->dp.h == 30) {
         // h = 30 (BASELINE.json configs[3]): walking class S <= 30 with the tile matrix in shared memory
         // (97 KB, one CTA per SM), standing class S <= 60 with it in the L2-resident scratch (380 KB)
-        if (h->dp.LB != 5) {
-            delete h;
-            return fail("h = 30 is instantiated for the reference limit structure only (exactly one pinned component)");
-        }
-        // walking class (<= 30 stance foot-stages): dense tile factor in shared memory (97 KB).  Standing class (<= 60):
-        // stage-wise Riccati backend (no 380 KB matrix), with a dense re-solve (matrix in the L2 scratch) of the few
-        // instances it does not certify.  BMPC_H30=dense / ric force one backend for both classes (experiments).
+        if (h->dp.LB == 6) {  // no pinned component: same three kernels with 6x6 tiles / 12 inputs per stage
+            rc = setup_variant<30, 30, 6, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
+                 setup_variant<30, 60, 6, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb) ||
+                 setup_variant<30, 60, 6, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
+        } else {
         const char* er = getenv("BMPC_H30");
         const std::string mode = er ? er : "hybrid";
         const char* en = getenv("BMPC_RIC_NT");
@@ -292,6 +290,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
                  (rnt == 32 ? setup_variant<30, 60, 5, 32, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb)
                             : setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb)) ||
                  setup_variant<30, 60, 5, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
+        }
     } else if (h->dp.LB == 5) {
         rc = (nww == 1   ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
               : nww == 5 ? setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)

@@ -84,3 +84,25 @@ def test_h30_mixed_contact_patterns_against_oracle():
         assert np.abs(out["controls"][i] - ct).max() / max(1.0, np.abs(ct).max()) <= U_RTOL, (i, S[i])
         assert np.abs(out["tau"][i] - tau).max() <= TAU_ATOL, (i, S[i])
     s.close()
+
+
+def test_h30_unpinned_limit_set_lb6():
+    """h = 30 with a limit set that pins no component (LB = 6: 6x6 tiles, 12 inputs per double-support stage),
+    parameter variant 2 of the golden fixtures, against the oracle."""
+    from conftest import variant_params
+    from oracle import reference_mpc as rm
+    from biped_mpc_py_b200 import BatchedMPC, synth
+    mpc, biped = variant_params(2, h=30)
+    n = 8
+    b = synth.make_batch(n, shard_index=15, mpc=mpc, biped=biped, extend=True, walking_prob=0.5)
+    s = BatchedMPC(mpc, biped, max_batch=n, extend_gait=True)
+    out = s.step_host(b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"], phase_k=b["phase_k"])
+    assert (out["status"] == 0).all(), out["status"]
+    assert set(b["gait"].tolist()) == {0, 1}
+    for i in range(n):
+        st, ct = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, biped, b["contact"][i], extend=True)
+        tau = rm.lowLevelControl(b["x_fb"][i], float(b["t"][i]), b["pf_w"][i].reshape(6, 1), b["q"][i], b["qd"][i], mpc, biped,
+                                 b["contact"][i], ct[0].reshape(-1, 1)).reshape(-1)
+        assert np.abs(out["controls"][i] - ct).max() / max(1.0, np.abs(ct).max()) <= U_RTOL, i
+        assert np.abs(out["tau"][i] - tau).max() <= TAU_ATOL, i
+    s.close()
