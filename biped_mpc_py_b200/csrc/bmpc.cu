@@ -260,48 +260,56 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         return 1;
     }
     int rc = 0;
-    // experiment knobs (threads per robot in each class); the defaults are the shipped configuration
-    const char* ew = getenv("BMPC_NW_WALK");
-    const char* es = getenv("BMPC_NT_STAND");
-    const int nww = ew ? atoi(ew) : 8, nts = es ? atoi(es) : 128;  // walking: robots per CTA; standing: threads per robot
+    // The shipped configuration of every class.  Building with -DBMPC_EXPERIMENTS adds the alternative instantiations the
+    // measurements in profiles/r1_summary.md were taken with (BMPC_NW_WALK = 1 | 5, BMPC_NT_STAND = 256, BMPC_H30 = dense | ric,
+    // BMPC_RIC_NT = 32), selected through environment variables.
+    const int sms = h->num_sms, mb = h->dp.mb;
+#ifdef BMPC_EXPERIMENTS
+    auto envi = [](const char* k, int dflt) { const char* v = getenv(k); return v ? atoi(v) : dflt; };
+    const int nww = envi("BMPC_NW_WALK", 8), nts = envi("BMPC_NT_STAND", 128), rnt = envi("BMPC_RIC_NT", 128);
+    const char* eh = getenv("BMPC_H30");
+    const std::string h30mode = eh ? eh : "hybrid";
+#endif
     if (h->dp.h == 30) {
-        // h = 30 (BASELINE.json configs[3]): walking class S <= 30 with the tile matrix in shared memory
-        // (97 KB, one CTA per SM), standing class S <= 60 with it in the L2-resident scratch (380 KB)
+        // h = 30 (BASELINE.json configs[3]).  Walking class (<= 30 stance foot-stages): dense tile factor in shared memory
+        // (97 KB).  Standing class (<= 60): stage-wise Riccati backend (no 380 KB matrix), with a dense re-solve (matrix in
+        // the L2 scratch) of the few instances it does not certify.
         if (h->dp.LB == 6) {  // no pinned component: same three kernels with 6x6 tiles / 12 inputs per stage
-            rc = setup_variant<30, 30, 6, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
-                 setup_variant<30, 60, 6, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb) ||
-                 setup_variant<30, 60, 6, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
+            rc = setup_variant<30, 30, 6, 256, 1>(h->bucket[0], sms, mb) ||
+                 setup_variant<30, 60, 6, 128, 1, false, true>(h->bucket[1], sms, mb) ||
+                 setup_variant<30, 60, 6, 256, 1, true>(h->fallback, sms, mb);
         } else {
-        const char* er = getenv("BMPC_H30");
-        const std::string mode = er ? er : "hybrid";
-        const char* en = getenv("BMPC_RIC_NT");
-        const int rnt = en ? atoi(en) : 128;
-        if (mode == "dense")
-            rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
-                 setup_variant<30, 60, 5, 256, 1, true>(h->bucket[1], h->num_sms, h->dp.mb);
-        else if (mode == "ric")
-            rc = (rnt == 32 ? (setup_variant<30, 30, 5, 32, 1, false, true>(h->bucket[0], h->num_sms, h->dp.mb) ||
-                               setup_variant<30, 60, 5, 32, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb))
-                            : (setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], h->num_sms, h->dp.mb) ||
-                               setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb))) ||
-                 setup_variant<30, 60, 5, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
-        else
-            rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], h->num_sms, h->dp.mb) ||
-                 (rnt == 32 ? setup_variant<30, 60, 5, 32, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb)
-                            : setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], h->num_sms, h->dp.mb)) ||
-                 setup_variant<30, 60, 5, 256, 1, true>(h->fallback, h->num_sms, h->dp.mb);
+#ifdef BMPC_EXPERIMENTS
+            if (h30mode == "dense")
+                rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], sms, mb) || setup_variant<30, 60, 5, 256, 1, true>(h->bucket[1], sms, mb);
+            else if (h30mode == "ric")
+                rc = (rnt == 32 ? (setup_variant<30, 30, 5, 32, 1, false, true>(h->bucket[0], sms, mb) ||
+                                   setup_variant<30, 60, 5, 32, 1, false, true>(h->bucket[1], sms, mb))
+                                : (setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], sms, mb) ||
+                                   setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], sms, mb))) ||
+                     setup_variant<30, 60, 5, 256, 1, true>(h->fallback, sms, mb);
+            else
+#endif
+                rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], sms, mb) ||
+                     setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], sms, mb) ||
+                     setup_variant<30, 60, 5, 256, 1, true>(h->fallback, sms, mb);
         }
     } else if (h->dp.LB == 5) {
-        rc = (nww == 1   ? setup_variant<10, 10, 5, 32, 1>(h->bucket[0], h->num_sms, h->dp.mb)
-              : nww == 5 ? setup_variant<10, 10, 5, 32, 5>(h->bucket[0], h->num_sms, h->dp.mb)
-                         : setup_variant<10, 10, 5, 32, 8>(h->bucket[0], h->num_sms, h->dp.mb)) ||
-             (nts == 256 ? setup_variant<10, 20, 5, 256, 1>(h->bucket[1], h->num_sms, h->dp.mb)
-                         : setup_variant<10, 20, 5, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb));
-        const char* ell = getenv("BMPC_LOWLAT");
-        if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, h->num_sms, h->dp.mb);
+#ifdef BMPC_EXPERIMENTS
+        if (nww == 1) rc = setup_variant<10, 10, 5, 32, 1>(h->bucket[0], sms, mb);
+        else if (nww == 5) rc = setup_variant<10, 10, 5, 32, 5>(h->bucket[0], sms, mb);
+        else
+#endif
+            rc = setup_variant<10, 10, 5, 32, 8>(h->bucket[0], sms, mb);  // walking: 8 robots per CTA, one warp each
+#ifdef BMPC_EXPERIMENTS
+        if (!rc && nts == 256) rc = setup_variant<10, 20, 5, 256, 1>(h->bucket[1], sms, mb);
+        else
+#endif
+            if (!rc) rc = setup_variant<10, 20, 5, 128, 1>(h->bucket[1], sms, mb);  // standing: one 128-thread CTA per robot
+        const char* ell = getenv("BMPC_LOWLAT");  // 0 disables the low-latency walking variant for batches <= 8
+        if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, sms, mb);
     } else {
-        rc = setup_variant<10, 10, 6, 32, 6>(h->bucket[0], h->num_sms, h->dp.mb) ||
-             setup_variant<10, 20, 6, 128, 1>(h->bucket[1], h->num_sms, h->dp.mb);
+        rc = setup_variant<10, 10, 6, 32, 6>(h->bucket[0], sms, mb) || setup_variant<10, 20, 6, 128, 1>(h->bucket[1], sms, mb);
     }
     if (rc) {
         delete h;
