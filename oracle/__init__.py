@@ -17,6 +17,10 @@ What it restates (all citations are into /root/reference/bipedalLocomotionMPC.py
   so its optimum is unique and solver independent: the oracle returns that
   optimum (interior point -> active-set polish -> KKT certificate).
 
+* ``highs_check.py``    - an independent second opinion on the solve: scipy's bundled HiGHS QP solver on the same
+  dense QP (objective agreement to 1e-8, never better than the certified optimum).
+* ``rollout.py``        - the closed-loop rules R1-R7 on the CPU (checker of ``bmpc_rollout``).
+
 Parity pinning: the reference has no tests or golden vectors.  The oracle is
 pinned two ways: (1) ``oracle/gen_golden.py`` imports the *real* reference module
 in the build container (with a stub ``cvxopt`` that captures the matrices the

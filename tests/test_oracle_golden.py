@@ -136,3 +136,29 @@ def test_exact_solver_agrees_with_independent_fullsize_ipm(golden):
         u_ipm = x_ipm[130:]
         assert iters < 60
         assert np.abs(u_ipm - u_exact).max() <= 5e-3 * max(1.0, np.abs(u_exact).max())
+
+
+def test_third_party_solver_agrees_with_the_certified_optimum():
+    """Independent second opinion: the HiGHS QP solver bundled with scipy, on the dense QP the reference hands
+    to cvxopt.  HiGHS stops at its own tolerances, so: same objective to 1e-8 relative, never better than the certified
+    optimum, forces within 0.2 N (the objective is flat in the forces: R = 1e-4)."""
+    from oracle import highs_check as hc, qp_exact
+    if not hc.available():
+        pytest.skip("scipy's bundled HiGHS is not importable here")
+    from biped_mpc_py_b200 import synth
+    mpc, biped = rm.MPCParams(), rm.BipedParams()
+    cases = []
+    pf0 = rm.getFootPositionWorld(rm.X_FB0, rm.Q0, biped).reshape(-1)
+    for c in G_CASES.values():
+        contact = rm.get_contact_sequence(c["t"], mpc) if c["gait"] == 1 else np.ones((mpc.h, 2))
+        cases.append((rm.X_FB0, c["t"], pf0, contact))
+    b = synth.make_batch(6, shard_index=41)
+    cases += [(b["x_fb"][i], float(b["t"][i]), b["foot"][i], b["contact"][i]) for i in range(6)]
+    for x, t, foot, contact in cases:
+        qp = rm.build_qp(x, t, foot, mpc, biped, contact)
+        z, obj, status = hc.solve_qp(qp["H"], qp["f"], qp["G"], qp["hv"], qp["A"], qp["b"])
+        ex = qp_exact.solve(qp["H"], qp["f"], qp["G"], qp["hv"], qp["A"], qp["b"])
+        assert status == "Optimal"
+        assert abs(obj - ex["obj"]) <= 1e-8 * max(1.0, abs(ex["obj"]))
+        assert ex["obj"] <= obj + 1e-9 * max(1.0, abs(obj))          # the certified point is never worse
+        assert np.abs(z[13 * mpc.h:] - ex["x"][13 * mpc.h:]).max() <= 0.2
