@@ -25,11 +25,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("BMPC_LIB_PATH", LIB_PATH)  # alternative builds of the same sources (compiler-flag experiments)
+    if not os.path.exists(path):
         raise LibraryMissing(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). biped_mpc_py_b200 has no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     dp, ip, up, vp = POINTER(c_double), POINTER(c_int32), POINTER(c_uint8), c_void_p
     lib.bmpc_create.argtypes = [POINTER(BmpcParams), c_int, c_int, POINTER(c_void_p)]
     lib.bmpc_create.restype = c_int
