@@ -194,38 +194,39 @@ __device__ __forceinline__ bool ric_factor_stage(const DevParams& p, const R r, 
     bool ok = true;
     if (NT == 32 || (threadIdx.x & (NT - 1)) < 32) {
         const int lane = threadIdx.x & 31;
+        constexpr int NR = (ntri + 31) / 32;
+        // this lane's entries (i >= j) of the lower triangle: decoded once, the same for every pivot
+        int ei[NR], ej[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const int e = lane + q * 32;
+            int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            if (i * (i + 1) / 2 > e) --i;
+            if ((i + 1) * (i + 2) / 2 <= e) ++i;
+            ei[q] = (e < ntri) ? i : -1;
+            ej[q] = e - i * (i + 1) / 2;
+        }
+        double* Gs = r.G();
 #pragma unroll 1
         for (int pv = 0; pv < nu; ++pv) {
-            const double gpp = r.G()[pv * NU + pv];
+            const double gpp = Gs[pv * NU + pv];
             ok = ok && (gpp > 0.0) && (gpp < 1e300);
             const double d = 1.0 / gpp;
-            constexpr int NR = (ntri + 31) / 32;
             double nv[NR];
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
-                const int e = lane + q * 32;
-                if (e < ntri) {
-                    int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-                    if (i * (i + 1) / 2 > e) --i;
-                    if ((i + 1) * (i + 2) / 2 <= e) ++i;
-                    const int j = e - i * (i + 1) / 2;  // j <= i
-                    const double gip = (i >= pv) ? r.G()[i * NU + pv] : r.G()[pv * NU + i];
-                    const double gpj = (j >= pv) ? r.G()[j * NU + pv] : r.G()[pv * NU + j];
-                    const double gij = r.G()[i * NU + j];
+                const int i = ei[q], j = ej[q];
+                if (i >= 0) {
+                    const double gip = (i >= pv) ? Gs[i * NU + pv] : Gs[pv * NU + i];
+                    const double gpj = (j >= pv) ? Gs[j * NU + pv] : Gs[pv * NU + j];
+                    const double gij = Gs[i * NU + j];
                     nv[q] = (i == pv && j == pv) ? -d : ((i == pv || j == pv) ? ((i == pv) ? gpj : gip) * d : gij - gip * gpj * d);
                 }
             }
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < NR; ++q) {
-                const int e = lane + q * 32;
-                if (e < ntri) {
-                    int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-                    if (i * (i + 1) / 2 > e) --i;
-                    if ((i + 1) * (i + 2) / 2 <= e) ++i;
-                    r.G()[i * NU + (e - i * (i + 1) / 2)] = nv[q];
-                }
-            }
+            for (int q = 0; q < NR; ++q)
+                if (ei[q] >= 0) Gs[ei[q] * NU + ej[q]] = nv[q];
             __syncwarp();
         }
     }
