@@ -218,12 +218,14 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b,
                                                v.d_scratch);
         if (b == 1 && h->fallback.fn) {
+            // instances of EITHER class that the stage-wise kernels did not certify: dense re-solve (handles any S <= 2h)
             const Variant& f = h->fallback;
-            collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_lists + (size_t)h->max_batch, h->d_counts + 1, io.status,
-                                                                       h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2);
+            for (int c = 0; c < 2; ++c)
+                collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_lists + (size_t)c * h->max_batch, h->d_counts + c, io.status,
+                                                                           h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2);
             const int fgrid = (std::min(n, f.resident) + f.per_cta - 1) / f.per_cta;
             f.fn<<<fgrid, f.threads, f.smem, st>>>(h->dp, io, h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2, f.d_scratch);
-            h->launches += 2;
+            h->launches += 3;
         }
         if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2 + b], st));
     }
@@ -268,19 +270,23 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
     auto envi = [](const char* k, int dflt) { const char* v = getenv(k); return v ? atoi(v) : dflt; };
     const int nww = envi("BMPC_NW_WALK", 8), nts = envi("BMPC_NT_STAND", 128), rnt = envi("BMPC_RIC_NT", 128);
     const char* eh = getenv("BMPC_H30");
-    const std::string h30mode = eh ? eh : "hybrid";
+    const std::string h30mode = eh ? eh : "ric";
 #endif
     if (h->dp.h == 30) {
-        // h = 30 (BASELINE.json configs[3]).  Walking class (<= 30 stance foot-stages): dense tile factor in shared memory
-        // (97 KB).  Standing class (<= 60): stage-wise Riccati backend (no 380 KB matrix), with a dense re-solve (matrix in
-        // the L2 scratch) of the few instances it does not certify.
+        // h = 30 (BASELINE.json configs[3]).  Both classes use the stage-wise Riccati backend (110 ms vs 135 ms dense for the
+        // walking class, 59 ms vs 223 ms for the standing class at 16,384 instances), followed by a dense re-solve (tile
+        // matrix in the L2 scratch) of the few instances it does not certify.
         if (h->dp.LB == 6) {  // no pinned component: same three kernels with 6x6 tiles / 12 inputs per stage
-            rc = setup_variant<30, 30, 6, 256, 1>(h->bucket[0], sms, mb) ||
+            rc = setup_variant<30, 30, 6, 128, 1, false, true>(h->bucket[0], sms, mb) ||
                  setup_variant<30, 60, 6, 128, 1, false, true>(h->bucket[1], sms, mb) ||
                  setup_variant<30, 60, 6, 256, 1, true>(h->fallback, sms, mb);
         } else {
 #ifdef BMPC_EXPERIMENTS
-            if (h30mode == "dense")
+            if (h30mode == "hybrid")
+                rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], sms, mb) ||
+                     setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], sms, mb) ||
+                     setup_variant<30, 60, 5, 256, 1, true>(h->fallback, sms, mb);
+            else if (h30mode == "dense")
                 rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], sms, mb) || setup_variant<30, 60, 5, 256, 1, true>(h->bucket[1], sms, mb);
             else if (h30mode == "ric")
                 rc = (rnt == 32 ? (setup_variant<30, 30, 5, 32, 1, false, true>(h->bucket[0], sms, mb) ||
@@ -290,7 +296,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
                      setup_variant<30, 60, 5, 256, 1, true>(h->fallback, sms, mb);
             else
 #endif
-                rc = setup_variant<30, 30, 5, 256, 1>(h->bucket[0], sms, mb) ||
+                rc = setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], sms, mb) ||
                      setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], sms, mb) ||
                      setup_variant<30, 60, 5, 256, 1, true>(h->fallback, sms, mb);
         }

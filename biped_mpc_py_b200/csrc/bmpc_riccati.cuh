@@ -18,6 +18,9 @@
 
 namespace bmpc {
 
+// row of entry e of the packed lower triangle of a 12 x 12 matrix
+__constant__ unsigned char TRI12_ROW[78] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 8, 9, 9, 9, 9, 9, 9, 9, 9, 9, 9, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11};
+
 template <int NT>
 __device__ __forceinline__ void rsync() {
     if constexpr (NT == 32) __syncwarp();
@@ -129,10 +132,7 @@ __device__ __forceinline__ void ric_step_P(const DevParams& p, const R r, int k,
     const double* Kb = r.K() + j0 * LB * 12;  // the stage's K rows are contiguous: [NUK][12]
 #pragma unroll 1
     for (int e = tid; e < 78; e += NT) {
-        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        if (a * (a + 1) / 2 > e) --a;
-        if ((a + 1) * (a + 2) / 2 <= e) ++a;
-        const int b = e - a * (a + 1) / 2;  // b <= a
+        const int a = TRI12_ROW[e], b = e - a * (a + 1) / 2;  // e = a(a+1)/2 + b, b <= a (table instead of a float square root)
         double v = r.PA()[a * 12 + b];
         if (a >= 6 && a < 9) v += dt * (ri[a - 6] * r.PA()[b] + ri[3 + a - 6] * r.PA()[12 + b] + ri[6 + a - 6] * r.PA()[24 + b]);
         if (a >= 9) v += dt * r.PA()[(3 + a - 9) * 12 + b];
