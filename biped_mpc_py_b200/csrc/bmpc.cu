@@ -12,6 +12,7 @@
 #include <string>
 
 #include "../../include/biped_mpc_b200.h"
+#include "bmpc_presolve.h"
 #include "bmpc_rollout.cuh"
 #include "bmpc_small.cuh"
 #include "bmpc_tick.cuh"
@@ -77,100 +78,9 @@ struct bmpc_handle {
 
 namespace {
 
-// Host-side presolve of the per-block inequality rows (MPC.py:220-271): which of the six
-// components [fx,fy,fz,mx,my,mz] are free, and which rows are implied by others for these
-// parameter values (dropping them does not change the feasible set).
 int build_dev_params(const bmpc_params& P, DevParams& d) {
-    memset(&d, 0, sizeof(d));
-    if (P.h != 10 && P.h != 30) return fail("horizon must be 10 or 30 (the instantiated kernels)");
-    d.h = P.h;
-    d.extend = P.extend_gait;
-    d.dt = P.dt;
-    d.kv = P.kv;
-    d.swing_height = P.swing_height;
-    d.mass = P.mass;
-    d.lt_eff = P.lt - 0.01;  // MPC.py:254
-    d.lh_eff = P.lh - 0.02;  // MPC.py:255
-    d.g = P.g;
-    d.mu = P.mu;
-    d.max_iter = P.max_iter > 0 ? P.max_iter : 40;
-    d.mu_tol = P.mu_tol > 0 ? P.mu_tol : 1e-7;
-    d.rd_tol = P.rd_tol > 0 ? P.rd_tol : 10.0;
-    d.gondzio = 1;
-    {
-        const char* eg = getenv("BMPC_GONDZIO_BELOW");  // run the centrality corrector only when the step length is below this
-        d.gondzio_below = eg ? atof(eg) : 0.95;  // measured: 1.722 M solves/s at 0.95 vs 1.696 M always (131,072 robots)
-    }
-    d.init_fz_frac = 0.2;   // start point: 20 % of the fz range, friction/moment components centred
-    d.mu0_scale = 0.1;      // initial complementarity = mu0_scale * mean slack
-    // polish rounds per attempt: long horizons have more weakly active rows that only show up as violations
-    // one round at a time (h = 30 instances needing 5-7 rounds were measured with tools/kernel_model.py)
-    d.polish_rounds = P.h > 10 ? 16 : 4;
-    {
-        const char* el = getenv("BMPC_LOCK");  // experiment knob: 3 = lockstep (default), 0 = with an extra step at instance start, 2 = none
-        d.lock_mode = el ? atoi(el) : 3;
-    }
-    d.warm_rounds = 6;      // polish rounds allowed to a warm-started tick before it falls back to the cold path
-    d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
-    memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));
-    memcpy(d.Q, P.Q, sizeof(d.Q));
-    memcpy(d.R, P.R, sizeof(d.R));
-    memcpy(d.kp, P.kp, sizeof(d.kp));
-    memcpy(d.kd, P.kd, sizeof(d.kd));
-    memcpy(d.inertia, P.inertia, sizeof(d.inertia));
-    memcpy(d.hip, P.hip_offset, sizeof(d.hip));
-    for (int c = 0; c < 3; ++c) {
-        d.lo6[c] = P.f_min[c];
-        d.hi6[c] = P.f_max[c];
-        d.lo6[3 + c] = P.tau_min[c];
-        d.hi6[3 + c] = P.tau_max[c];
-    }
-    if (!(P.dt > 0) || !(P.mass > 0) || !(P.mu >= 0)) return fail("dt, mass must be positive and mu non-negative");
-    for (int c = 0; c < 6; ++c) {
-        if (!(d.hi6[c] >= d.lo6[c])) return fail("empty box: a *_max is below its *_min");
-        if (d.hi6[c] > d.lo6[c])
-            d.comps[d.LB++] = c;
-        else
-            d.pinned[d.npinned++] = c;
-    }
-    if (d.LB != 5 && d.LB != 6)
-        return fail("unsupported limits: at most one of the six force/moment components may be pinned (min == max)");
-    bool f_free = true;
-    for (int c = 0; c < 3; ++c) f_free = f_free && (d.hi6[c] > d.lo6[c]);
-    auto local = [&](int comp) {
-        for (int c = 0; c < d.LB; ++c)
-            if (d.comps[c] == comp) return c;
-        return -1;
-    };
-    int mb = 0;
-    auto add = [&](int kind, int arg) {
-        d.row_kind[mb] = kind;
-        d.row_arg[mb] = arg;
-        ++mb;
-    };
-    const bool pyramid = f_free && P.mu > 0;
-    for (int c = 0; c < 6; ++c) {  // lower bounds
-        if (local(c) < 0) continue;
-        bool keep = true;
-        if (pyramid && c == 2 && d.lo6[2] <= 0) keep = false;                       // |fx| <= mu fz => fz >= 0
-        if (pyramid && c < 2 && d.lo6[c] <= -P.mu * d.hi6[2]) keep = false;          // fx >= -mu fz >= -mu fz_max
-        if (keep) add(ROW_LO, local(c));
-    }
-    for (int c = 0; c < 6; ++c) {  // upper bounds
-        if (local(c) < 0) continue;
-        bool keep = true;
-        if (pyramid && c < 2 && d.hi6[c] >= P.mu * d.hi6[2]) keep = false;           // fx <= mu fz <= mu fz_max
-        if (keep) add(ROW_HI, local(c));
-    }
-    for (int r = 0; r < 4; ++r) {  // friction pyramid, MPC.py:220-229
-        bool keep = true;
-        // -fx - mu fz <= 0 is implied by fx >= 0 and fz >= 0 (reference defaults: f_min = 0)
-        if (r >= 2 && d.lo6[r - 2] >= 0 && d.lo6[2] >= 0) keep = false;
-        if (keep) add(ROW_FRIC, r);
-    }
-    add(ROW_LINE, 0);  // MPC.py:258-263
-    add(ROW_LINE, 1);
-    d.mb = mb;
+    std::string err;
+    if (build_dev_params_impl(P, d, err)) return fail(err);
     return 0;
 }
 

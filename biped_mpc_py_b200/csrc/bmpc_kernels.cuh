@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define BMPC_HD __host__ __device__
+
 namespace bmpc {
 
 constexpr int MAXROWS = 18;  // per-block inequality rows: 2*6 bounds + 4 friction + 2 line-foot
@@ -85,19 +87,19 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  : "memory");
 }
 
-__device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* c) {
+BMPC_HD __forceinline__ void mat3_mul(const double* a, const double* b, double* c) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
 }
-__device__ __forceinline__ void mat3_tmul(const double* a, const double* b, double* c) {  // a' * b
+BMPC_HD __forceinline__ void mat3_tmul(const double* a, const double* b, double* c) {  // a' * b
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) c[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
 }
-__device__ __forceinline__ bool mat3_inv(const double* a, double* r) {
+BMPC_HD __forceinline__ bool mat3_inv(const double* a, double* r) {
     double c0 = a[4] * a[8] - a[5] * a[7], c1 = a[5] * a[6] - a[3] * a[8], c2 = a[3] * a[7] - a[4] * a[6];
     double det = a[0] * c0 + a[1] * c1 + a[2] * c2;
     double id = 1.0 / det;
@@ -113,7 +115,7 @@ __device__ __forceinline__ bool mat3_inv(const double* a, double* r) {
     return isfinite(id);
 }
 // eul2rotm of MPC.py:111-138: Rz(e[2]) Ry(e[1]) Rx(e[0])
-__device__ __forceinline__ void eul2rotm(const double* e, double* R) {
+BMPC_HD __forceinline__ void eul2rotm(const double* e, double* R) {
     double sr, cr, sp, cp, sy, cy;
     sincos(e[0], &sr, &cr);
     sincos(e[1], &sp, &cp);
@@ -132,7 +134,7 @@ __device__ __forceinline__ void eul2rotm(const double* e, double* R) {
 // ------------------------------------------------------------------------------------
 // leg Jacobian (MPC.py:306-365) and low-level torque map (MPC.py:426-470) for one leg
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void leg_jacobian(const double* q, double side, double* J /*6x5 row-major*/) {
+BMPC_HD __forceinline__ void leg_jacobian(const double* q, double side, double* J /*6x5 row-major*/) {
     double s0, c0, s1, c1, s2, c2, s23, c23, s234, c234;
     sincos(q[0], &s0, &c0);
     sincos(q[1], &s1, &c1);
@@ -167,7 +169,7 @@ __device__ __forceinline__ void leg_jacobian(const double* q, double side, doubl
 }
 
 // tau_leg[5] for one leg.  R = eul2rotm(x_fb[0:3]); u = [f1,f2,m1,m2] first-stage input.
-__device__ __noinline__ void lowlevel_leg(const DevParams& p, const double* x_fb, double t, const double* pf_w,
+BMPC_HD __noinline__ void lowlevel_leg(const DevParams& p, const double* x_fb, double t, const double* pf_w,
                                     const double* q, const double* qd, const double* R, int leg, double c_leg,
                                     const double* u, double* tau_leg) {
     const double side = (leg == 0) ? 1.0 : -1.0;

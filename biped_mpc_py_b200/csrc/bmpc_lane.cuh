@@ -1,0 +1,937 @@
+// Lane-per-robot MPC tick: ONE THREAD solves one robot, 32 robots per warp execute the same instruction stream.
+//
+// Why: the warp-per-robot kernel (bmpc_tick.cuh) is bound by instruction delivery — every warp walks a 40 KB loop at
+// its own position for one 50-variable problem, ~12 issued warp instructions per useful FP64 FMA lane-op
+// (profiles/r1_summary.md).  Here an instruction serves 32 robots, there is no cross-lane communication and no
+// barrier, and the linear algebra is the stage-wise (Riccati) form of the same QP: the contact-reduced problem is an
+// LQR problem  X_i = A_i X_{i-1} + B_i u_i + c_i  (MPC.py:165-184, 206-214) with block-diagonal input weights, so a
+// backward sweep over the 12x12 cost-to-go factors  M = Hc + blockdiag(Cb' D Cb)  in O(h) and Hc is never formed.
+// Same algorithm as the tick kernel otherwise (Mehrotra + Gondzio interior point to a loose target, active-set polish,
+// KKT certificate; the per-block null-space / multiplier checks are the SAME functions, bmpc_polish.cuh), written as
+// plain scalar C++ so that the identical source is unit-tested on the CPU (tests/lane_host.cu) against the oracle.
+//
+// Per-robot work arrays live in a global workspace interleaved by lane (element i of lane l at ws[i*32 + l]: every
+// access of a warp is one fully used 256-byte line pair); on the host the stride is 1.
+// A robot this path does not certify keeps status 1 and is re-solved by the warp-per-robot kernels (bmpc.cu).
+#pragma once
+#include "bmpc_kernels.cuh"
+#include "bmpc_polish.cuh"
+
+namespace bmpc {
+
+#ifdef __CUDA_ARCH__
+#define BMPC_LS 32
+#else
+#define BMPC_LS 1
+#endif
+
+struct SV {  // strided view of one lane's slice of the workspace
+    double* p;
+    BMPC_HD __forceinline__ double& operator[](int i) const { return p[(size_t)i * BMPC_LS]; }
+    BMPC_HD __forceinline__ SV operator+(int o) const { return SV{p + (size_t)o * BMPC_LS}; }
+};
+
+template <int HZ, int NF, int LB>
+struct LaneL {
+    static constexpr int NU = NF * LB, S = HZ * NF, N = NU * HZ, MBM = 12, M = S * MBM, E = LB * LB;
+    static constexpr int o_u = 0, o_du = o_u + N, o_x = o_du + N, o_up = o_x + N, o_rd = o_up + N, o_pp = o_rd + N,
+                         o_tv = o_pp + N, o_hd = o_tv + N;
+    static constexpr int o_rs = o_hd + N, o_rl = o_rs + M, o_rdw = o_rl + M, o_rp = o_rdw + M, o_rc = o_rp + M,
+                         o_rw = o_rc + M;
+    static constexpr int o_P = o_rw + M;                 // 12 x 12 cost-to-go
+    static constexpr int o_PB = o_P + 144;               // 12 x NU
+    static constexpr int o_F = o_PB + 12 * NU;           // NU x 12
+    static constexpr int o_G = o_F + 12 * NU;            // NU x NU
+    static constexpr int o_K = o_G + NU * NU;            // per stage NU x 12 feedback gains
+    static constexpr int o_Lc = o_K + HZ * NU * 12;      // per stage Cholesky factor of G (reciprocal diagonal)
+    static constexpr int o_Rt = o_Lc + HZ * NU * NU;     // per stage input weights
+    static constexpr int o_Bm = o_Rt + HZ * NU * NU;     // per stage 6 x NU input maps in use (B, or B N in the polish)
+    static constexpr int o_B0 = o_Bm + HZ * 6 * NU;      // per stage 6 x NU input maps of the problem
+    static constexpr int o_c = o_B0 + HZ * 6 * NU;       // per stage affine term (omega, v rows)
+    static constexpr int o_rinv = o_c + HZ * 6;
+    static constexpr int o_xref = o_rinv + HZ * 9;
+    static constexpr int o_E = o_xref + HZ * 12;         // Q (X_i - xref_i)
+    static constexpr int o_Nn = o_E + HZ * 12;           // polish: null-space blocks
+    static constexpr int total = o_Nn + S * E;
+};
+
+template <int HZ, int NF, int LB>
+struct LaneSolver {
+    using L = LaneL<HZ, NF, LB>;
+    static constexpr int NU = L::NU, S = L::S, N = L::N, E = L::E;
+    const DevParams& p;
+    SV ws;
+    double x_fb[12];
+    double Cb[L::MBM * LB], rb[L::MBM], Rd[2][LB];
+    int fo[S];  // foot of every block (stage-major)
+    int mb, m;
+    double dt;
+
+    BMPC_HD LaneSolver(const DevParams& pp, SV w) : p(pp), ws(w) {}
+
+    // ---- objective gradient  Hc u + g  by a rollout and an adjoint sweep; optionally writes the states -------------
+    BMPC_HD void grad(SV u, SV out, double* states) {
+        double z[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) z[a] = x_fb[a];
+#pragma unroll 1
+        for (int i = 0; i < HZ; ++i) {
+            SV ri = ws + (L::o_rinv + 9 * i), B = ws + (L::o_B0 + 6 * NU * i), c = ws + (L::o_c + 6 * i), ui = u + NU * i;
+            double acc[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[k] = c[k];
+#pragma unroll 1
+            for (int col = 0; col < NU; ++col) {
+                const double uc = ui[col];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc[k] += B[k * NU + col] * uc;
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                z[a] += dt * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
+                z[3 + a] += dt * z[9 + a];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) z[6 + k] += acc[k];
+            SV Ei = ws + (L::o_E + 12 * i), xr = ws + (L::o_xref + 12 * i);
+#pragma unroll
+            for (int a = 0; a < 12; ++a) Ei[a] = p.Q[a] * (z[a] - xr[a]);
+            if (states) {
+#pragma unroll
+                for (int a = 0; a < 12; ++a) states[13 * i + a] = z[a];
+                states[13 * i + 12] = 1.0;
+            }
+        }
+        double lam[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) lam[a] = 0.0;
+#pragma unroll 1
+        for (int i = HZ - 1; i >= 0; --i) {
+            SV ri = ws + (L::o_rinv + 9 * i), B = ws + (L::o_B0 + 6 * NU * i), Ei = ws + (L::o_E + 12 * i), ui = u + NU * i,
+               oi = out + NU * i;
+#pragma unroll
+            for (int a = 0; a < 12; ++a) lam[a] += Ei[a];
+#pragma unroll 1
+            for (int col = 0; col < NU; ++col) {
+                double acc = Rd[fo[i * NF + col / LB]][col % LB] * ui[col];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc += B[k * NU + col] * lam[6 + k];
+                oi[col] = acc;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                lam[6 + k] += dt * (ri[k] * lam[0] + ri[3 + k] * lam[1] + ri[6 + k] * lam[2]);
+                lam[9 + k] += dt * lam[3 + k];
+            }
+        }
+    }
+
+    // P <- A_i' P A_i  (A = I + dt E: a column operation, then a row operation)
+    BMPC_HD void congruence(SV P, SV ri) {
+        double r9[9];
+#pragma unroll
+        for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
+#pragma unroll 1
+        for (int r = 0; r < 12; ++r) {
+            const double p0 = P[r * 12], p1 = P[r * 12 + 1], p2 = P[r * 12 + 2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                P[r * 12 + 6 + k] += p0 * r9[k] + p1 * r9[3 + k] + p2 * r9[6 + k];
+                P[r * 12 + 9 + k] += dt * P[r * 12 + 3 + k];
+            }
+        }
+#pragma unroll 1
+        for (int c = 0; c < 12; ++c) {
+            const double p0 = P[c], p1 = P[12 + c], p2 = P[24 + c];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                P[(6 + k) * 12 + c] += p0 * r9[k] + p1 * r9[3 + k] + p2 * r9[6 + k];
+                P[(9 + k) * 12 + c] += dt * P[(3 + k) * 12 + c];
+            }
+        }
+    }
+
+    // ---- backward Riccati sweep: factors  blockdiag(Rt) + B' (state cost) B  in stage-wise form --------------------
+    BMPC_HD bool factor() {
+        SV P = ws + L::o_P, PB = ws + L::o_PB, F = ws + L::o_F, G = ws + L::o_G;
+#pragma unroll 1
+        for (int e = 0; e < 144; ++e) P[e] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 12; ++a) P[a * 13] = p.Q[a];
+#pragma unroll 1
+        for (int i = HZ - 1; i >= 0; --i) {
+            SV B = ws + (L::o_Bm + 6 * NU * i), Rt = ws + (L::o_Rt + NU * NU * i), ri = ws + (L::o_rinv + 9 * i);
+            SV K = ws + (L::o_K + NU * 12 * i), Lc = ws + (L::o_Lc + NU * NU * i);
+            // PB = P[:, 6:12] B
+#pragma unroll 1
+            for (int r = 0; r < 12; ++r) {
+                double pr[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) pr[k] = P[r * 12 + 6 + k];
+#pragma unroll 1
+                for (int c = 0; c < NU; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc += pr[k] * B[k * NU + c];
+                    PB[r * NU + c] = acc;
+                }
+            }
+            // G = Rt + B' PB[6:12, :]   (lower triangle), then its Cholesky factor in place
+#pragma unroll 1
+            for (int a = 0; a < NU; ++a) {
+                double ba[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ba[k] = B[k * NU + a];
+#pragma unroll 1
+                for (int b = 0; b <= a; ++b) {
+                    double acc = Rt[a * NU + b];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc += ba[k] * PB[(6 + k) * NU + b];
+                    G[a * NU + b] = acc;
+                }
+            }
+#pragma unroll 1
+            for (int j = 0; j < NU; ++j) {
+                double d = G[j * NU + j];
+#pragma unroll 1
+                for (int k = 0; k < j; ++k) d -= Lc[j * NU + k] * Lc[j * NU + k];
+                if (!(d > 0.0) || !(d < 1e300)) return false;
+                const double r = 1.0 / sqrt(d);
+                Lc[j * NU + j] = r;
+#pragma unroll 1
+                for (int a = j + 1; a < NU; ++a) {
+                    double v = G[a * NU + j];
+#pragma unroll 1
+                    for (int k = 0; k < j; ++k) v -= Lc[a * NU + k] * Lc[j * NU + k];
+                    Lc[a * NU + j] = v * r;
+                }
+            }
+            // F = PB' A  (NU x 12), K = inv(G) F
+#pragma unroll 1
+            for (int c = 0; c < NU; ++c) {
+                double f[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) f[j] = PB[j * NU + c];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    f[6 + k] += dt * (f[0] * ri[k] + f[1] * ri[3 + k] + f[2] * ri[6 + k]);
+                    f[9 + k] += dt * f[3 + k];
+                }
+#pragma unroll
+                for (int j = 0; j < 12; ++j) F[c * 12 + j] = f[j];
+            }
+#pragma unroll 1
+            for (int j = 0; j < 12; ++j) {
+#pragma unroll 1
+                for (int a = 0; a < NU; ++a) {  // forward
+                    double v = F[a * 12 + j];
+#pragma unroll 1
+                    for (int k = 0; k < a; ++k) v -= Lc[a * NU + k] * K[k * 12 + j];
+                    K[a * 12 + j] = v * Lc[a * NU + a];
+                }
+#pragma unroll 1
+                for (int a = NU - 1; a >= 0; --a) {  // backward
+                    double v = K[a * 12 + j];
+#pragma unroll 1
+                    for (int k = a + 1; k < NU; ++k) v -= Lc[k * NU + a] * K[k * 12 + j];
+                    K[a * 12 + j] = v * Lc[a * NU + a];
+                }
+            }
+            if (i == 0) break;
+            // P <- Q + A' P A - F' K
+            congruence(P, ri);
+#pragma unroll 1
+            for (int r = 0; r < 12; ++r) {
+#pragma unroll 1
+                for (int c = 0; c <= r; ++c) {
+                    double acc = 0.5 * (P[r * 12 + c] + P[c * 12 + r]);
+#pragma unroll 1
+                    for (int a = 0; a < NU; ++a) acc -= F[a * 12 + r] * K[a * 12 + c];
+                    P[r * 12 + c] = acc;
+                    P[c * 12 + r] = acc;
+                }
+                P[r * 13] += p.Q[r];
+            }
+        }
+        return true;
+    }
+
+    // x <- inv(M) x  with the factor of the last factor() call
+    BMPC_HD void solve(SV x) {
+        double pv[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) pv[a] = 0.0;
+#pragma unroll 1
+        for (int i = HZ - 1; i >= 0; --i) {
+            SV B = ws + (L::o_Bm + 6 * NU * i), ri = ws + (L::o_rinv + 9 * i), K = ws + (L::o_K + NU * 12 * i), xi = x + NU * i;
+            double t[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[k] = dt * (ri[k] * pv[0] + ri[3 + k] * pv[1] + ri[6 + k] * pv[2]);
+            double np[12];
+#pragma unroll
+            for (int a = 0; a < 12; ++a) np[a] = pv[a];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) np[6 + k] += t[k], np[9 + k] += dt * pv[3 + k];
+#pragma unroll 1
+            for (int c = 0; c < NU; ++c) {
+                double g = -xi[c];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) g += B[k * NU + c] * pv[6 + k];
+                xi[c] = g;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) np[j] -= K[c * 12 + j] * g;
+            }
+#pragma unroll
+            for (int a = 0; a < 12; ++a) pv[a] = np[a];
+        }
+        double z[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) z[a] = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < HZ; ++i) {
+            SV B = ws + (L::o_Bm + 6 * NU * i), ri = ws + (L::o_rinv + 9 * i), K = ws + (L::o_K + NU * 12 * i),
+               Lc = ws + (L::o_Lc + NU * NU * i), xi = x + NU * i;
+#pragma unroll 1
+            for (int a = 0; a < NU; ++a) {
+                double v = xi[a];
+#pragma unroll 1
+                for (int k = 0; k < a; ++k) v -= Lc[a * NU + k] * xi[k];
+                xi[a] = v * Lc[a * NU + a];
+            }
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+            for (int a = NU - 1; a >= 0; --a) {
+                double v = xi[a];
+#pragma unroll 1
+                for (int k = a + 1; k < NU; ++k) v -= Lc[k * NU + a] * xi[k];
+                xi[a] = v * Lc[a * NU + a];
+            }
+#pragma unroll 1
+            for (int a = 0; a < NU; ++a) {
+                double v = xi[a];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) v += K[a * 12 + j] * z[j];
+                v = -v;
+                xi[a] = v;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc[k] += B[k * NU + a] * v;
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                z[a] += dt * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
+                z[3 + a] += dt * z[9 + a];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) z[6 + k] += acc[k];
+        }
+    }
+
+    BMPC_HD __forceinline__ double cdot(int k, SV v) const {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < LB; ++c) acc += Cb[k * LB + c] * v[c];
+        return acc;
+    }
+    // out_i = sign * (base_i) + (C' w)_i
+    BMPC_HD void gather(SV w, SV base, double bscale, SV out) {
+#pragma unroll 1
+        for (int j = 0; j < S; ++j) {
+            double acc[LB];
+#pragma unroll
+            for (int c = 0; c < LB; ++c) acc[c] = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < mb; ++k) {
+                const double wk = w[j * mb + k];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) acc[c] += Cb[k * LB + c] * wk;
+            }
+#pragma unroll
+            for (int c = 0; c < LB; ++c) out[j * LB + c] = (bscale != 0.0 ? bscale * base[j * LB + c] : 0.0) + acc[c];
+        }
+    }
+
+    // ---- the whole tick -------------------------------------------------------------------------------------------
+    BMPC_HD void run(const IoPtrs& io, int inst) {
+        mb = p.mb;
+        m = S * mb;
+        dt = p.dt;
+        SV uv = ws + L::o_u, duv = ws + L::o_du, xv = ws + L::o_x, upv = ws + L::o_up, rdv = ws + L::o_rd, ppv = ws + L::o_pp,
+           tvp = ws + L::o_tv, hd = ws + L::o_hd;
+        SV r_s = ws + L::o_rs, r_l = ws + L::o_rl, r_d = ws + L::o_rdw, r_p = ws + L::o_rp, r_c = ws + L::o_rc, r_w = ws + L::o_rw;
+        SV Nn = ws + L::o_Nn;
+
+        // ---- 0. inputs; this path takes robots with exactly NF stance feet in every stage ----
+        bool bad = mb > L::MBM;
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+            x_fb[a] = io.x_fb[(size_t)inst * 12 + a];
+            bad = bad || !isfinite(x_fb[a]);
+        }
+        double foot[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            foot[a] = io.foot[(size_t)inst * 6 + a];
+            bad = bad || !isfinite(foot[a]);
+        }
+        int cont0[2];
+        int blockOf[2 * HZ];
+        {
+            int j = 0;
+#pragma unroll 1
+            for (int s = 0; s < HZ; ++s) {
+                int cnt = 0;
+                for (int l = 0; l < 2; ++l) {
+                    const int c = io.contact[(size_t)inst * 2 * HZ + 2 * s + l] ? 1 : 0;
+                    if (s == 0) cont0[l] = c;
+                    blockOf[2 * s + l] = -1;
+                    if (c) {
+                        if (cnt < NF) fo[j] = l, blockOf[2 * s + l] = j, ++j;
+                        ++cnt;
+                    }
+                }
+                if (cnt != NF) bad = true, j = (s + 1) * NF;
+            }
+        }
+        if (bad) {  // not this path's robot (or bad input): the warp-per-robot kernels take it
+            io.status[inst] = 1;
+            io.iters[inst] = 0;
+            return;
+        }
+        const int phase_k = io.phase_k[inst];
+
+        // ---- 1. references, per-stage dynamics and input maps (MPC.py:61-109, 148-185) ----
+        double rotn[9], footv[18], ub[LB];
+        {
+            const double hh = (double)p.h;
+            const double ex = p.kv * (x_fb[3] - p.x_cmd[3]), ey = p.kv * (x_fb[4] - p.x_cmd[4]);
+            const double x1 = x_fb[3] + x_fb[9] * 1 / 2 * hh / 2 * dt + ex;
+            const double x2 = x_fb[3] + x_fb[9] * 1 / 2 * hh * dt + ex;
+            const double y1 = x_fb[4] + x_fb[10] * 1 / 2 * hh / 2 * dt + ey;
+            const double y2 = x_fb[10] + x_fb[10] * 1 / 2 * hh * dt + ey;  // MPC.py:87 starts from x_fb[10]
+            for (int c = 0; c < 6; ++c) footv[c] = foot[c];
+            footv[6] = x1, footv[7] = y1, footv[8] = 0.0, footv[9] = x1, footv[10] = y1, footv[11] = 0.0;
+            footv[12] = x2, footv[13] = y2, footv[14] = 0.0, footv[15] = x2, footv[16] = y2, footv[17] = 0.0;
+            eul2rotm(x_fb, rotn);
+            double u6[6];
+            for (int c = 0; c < 6; ++c) {
+                const double lo = p.lo6[c], hi = p.hi6[c];
+                const double v0 = fmin(fmax(0.0, lo + 0.1 * (hi - lo)), hi - 0.1 * (hi - lo));
+                u6[c] = (hi > lo) ? v0 : lo;
+            }
+            u6[2] = p.lo6[2] + p.init_fz_frac * (p.hi6[2] - p.lo6[2]);
+            for (int c = 0; c < 2; ++c) {
+                const double lo = fmax(p.lo6[c], -p.mu * u6[2]), hi = fmin(p.hi6[c], p.mu * u6[2]);
+                if (p.hi6[c] > p.lo6[c]) u6[c] = 0.5 * (lo + hi);
+            }
+            for (int c = 0; c < LB; ++c) ub[c] = u6[p.comps[c]];
+            for (int l = 0; l < 2; ++l)
+                for (int c = 0; c < LB; ++c) {
+                    const int ca = p.comps[c];
+                    Rd[l][c] = p.R[(ca < 3) ? (3 * l + ca) : (6 + 3 * l + ca - 3)];
+                }
+        }
+        const double vm = dt / p.mass;
+        bool singular = false;
+#pragma unroll 1
+        for (int k = 0; k < HZ; ++k) {
+            const int kk = phase_k % 5;
+            int sel = 0;
+            if (cont0[0] + cont0[1] == 1) sel = (k < 5 - kk) ? 0 : ((k < 10 - kk) ? 1 : 2);
+            double xr[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) xr[i] = (k == 0) ? x_fb[i] : p.x_cmd[i];
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                    if (p.x_cmd[i + 6] != 0.0) xr[i] = x_fb[i] + p.x_cmd[i + 6] * (k * dt);
+            }
+            SV xref = ws + (L::o_xref + 12 * k);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) xref[i] = xr[i];
+            double sz, cz, sy, cy, sx, cx;  // dynamics read x[0] as yaw, x[1] pitch, x[2] roll (MPC.py:151-153)
+            sincos(xr[0], &sz, &cz);
+            sincos(xr[1], &sy, &cy);
+            sincos(xr[2], &sx, &cx);
+            double rot[9];  // Rx(roll) Ry(pitch) Rz(yaw)  (extrinsic 'zyx', MPC.py:156)
+            rot[0] = cy * cz, rot[1] = -cy * sz, rot[2] = sy;
+            rot[3] = sx * sy * cz + cx * sz, rot[4] = -sx * sy * sz + cx * cz, rot[5] = -sx * cy;
+            rot[6] = -cx * sy * cz + sx * sz, rot[7] = cx * sy * sz + sx * cz, rot[8] = cx * cy;
+            double tmp[9], iw[9], ii[9];
+            mat3_mul(p.inertia, rot, tmp);
+            mat3_tmul(rot, tmp, iw);
+            if (!mat3_inv(iw, ii)) singular = true;
+            const double icp = 1.0 / cy;
+            if (!isfinite(icp) || fabs(cy) < 1e-9) singular = true;
+            SV ri = ws + (L::o_rinv + 9 * k);
+            ri[0] = cz * icp, ri[1] = sz * icp, ri[2] = 0.0;
+            ri[3] = -sz, ri[4] = cz, ri[5] = 0.0;
+            ri[6] = cz * sy * icp, ri[7] = sz * sy * icp, ri[8] = 1.0;
+            double cw[6] = {0, 0, 0, 0, 0, 0};
+            SV B0 = ws + (L::o_B0 + 6 * NU * k);
+            for (int li = 0; li < NF; ++li) {
+                const int l = fo[k * NF + li];
+                const double* fr = footv + 6 * sel + 3 * l;
+                const double r0 = fr[0] - xr[3], r1 = fr[1] - xr[4], r2 = fr[2] - xr[5];
+                double B[18];  // dt Iw^{-1} [skew(r) | I]  (MPC.py:174-179, 184)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double i0 = ii[3 * a], i1 = ii[3 * a + 1], i2 = ii[3 * a + 2];
+                    B[6 * a + 0] = dt * (i1 * r2 - i2 * r1);
+                    B[6 * a + 1] = dt * (i2 * r0 - i0 * r2);
+                    B[6 * a + 2] = dt * (i0 * r1 - i1 * r0);
+                    B[6 * a + 3] = dt * i0, B[6 * a + 4] = dt * i1, B[6 * a + 5] = dt * i2;
+                }
+                for (int a = 0; a < 3; ++a) {
+                    for (int c = 0; c < LB; ++c) {
+                        B0[a * NU + li * LB + c] = B[6 * a + p.comps[c]];
+                        B0[(3 + a) * NU + li * LB + c] = (p.comps[c] == a) ? vm : 0.0;
+                    }
+                    for (int c = 0; c < p.npinned; ++c) {
+                        cw[a] += B[6 * a + p.pinned[c]] * p.lo6[p.pinned[c]];
+                        if (p.pinned[c] == a) cw[3 + a] += vm * p.lo6[p.pinned[c]];
+                    }
+                }
+            }
+            cw[5] -= p.g * dt;
+            SV cc = ws + (L::o_c + 6 * k);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) cc[a] = cw[a];
+        }
+        if (singular) {
+            io.status[inst] = 1;
+            io.iters[inst] = 0;
+            return;
+        }
+        // per-block inequality rows in block coordinates (MPC.py:220-271), the same for every block
+        for (int k = 0; k < mb; ++k) {
+            const int kind = p.row_kind[k], arg = p.row_arg[k];
+            double f6[6] = {0, 0, 0, 0, 0, 0};
+            double rhs = 0.0;
+            if (kind == ROW_LO) {
+                f6[p.comps[arg]] = -1.0;
+                rhs = -p.lo6[p.comps[arg]];
+            } else if (kind == ROW_HI) {
+                f6[p.comps[arg]] = 1.0;
+                rhs = p.hi6[p.comps[arg]];
+            } else if (kind == ROW_FRIC) {
+                f6[arg & 1] = (arg < 2) ? 1.0 : -1.0;
+                f6[2] = -p.mu;
+            } else {
+                const double len = (arg == 0) ? p.lh_eff : p.lt_eff;
+                const double sg = (arg == 0) ? 1.0 : -1.0;
+                f6[0] = -len * rotn[2], f6[1] = -len * rotn[5], f6[2] = -len * rotn[8];
+                f6[3] = sg * rotn[1], f6[4] = sg * rotn[4], f6[5] = sg * rotn[7];
+            }
+            for (int c = 0; c < p.npinned; ++c) rhs -= f6[p.pinned[c]] * p.lo6[p.pinned[c]];
+            for (int c = 0; c < LB; ++c) Cb[k * LB + c] = f6[p.comps[c]];
+            rb[k] = rhs;
+        }
+
+        // ---- 2. interior point ----
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) uv[i] = 0.0;
+        grad(uv, tvp, nullptr);  // g = gradient at u = 0
+        double gs = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) gs = fmax(gs, fabs(tvp[i]));
+        gs += 1.0;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) uv[i] = ub[i % LB];
+        double part = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < mb; ++k) {
+            double sl = rb[k];
+            for (int c = 0; c < LB; ++c) sl -= Cb[k * LB + c] * ub[c];
+            if (!(sl > 1e-3)) sl = 1.0;
+            for (int j = 0; j < S; ++j) r_s[j * mb + k] = sl;
+            part += sl * (double)S;
+        }
+        const double mu0 = p.mu0_scale * part / (double)m;
+#pragma unroll 1
+        for (int r = 0; r < m; ++r) r_l[r] = mu0 / r_s[r];
+#pragma unroll 1
+        for (int e = 0; e < HZ * 6 * NU; ++e) ws[L::o_Bm + e] = ws[L::o_B0 + e];
+
+        const double mu_target = p.mu_tol * gs;
+        int status = 1, it = 0;
+        double mu = 0.0, rdmax = 0.0;
+        bool rd_fresh = false;
+#pragma unroll 1
+        while (true) {
+            if (it >= p.max_iter) {
+                status = 1;
+                break;
+            }
+            ++it;
+            part = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < S; ++j)
+#pragma unroll 1
+                for (int k = 0; k < mb; ++k) {
+                    const int r = j * mb + k;
+                    const double s = r_s[r], l = r_l[r];
+                    const double d = l / s, rp = cdot(k, uv + j * LB) + s - rb[k];
+                    r_d[r] = d;
+                    r_p[r] = rp;
+                    r_w[r] = d * rp - l;
+                    part += s * l;
+                }
+            if (!rd_fresh) {
+                grad(uv, tvp, nullptr);
+                gather(r_l, tvp, 1.0, rdv);
+                rdmax = 0.0;
+#pragma unroll 1
+                for (int i = 0; i < N; ++i) rdmax = fmax(rdmax, fabs(rdv[i]));
+                rd_fresh = true;
+            }
+            mu = part / (double)m;
+            if (mu <= mu_target && rdmax <= p.rd_tol * mu_target) {
+                status = 0;
+                break;
+            }
+            // stage input weights  R + Cb' diag(d_j) Cb  per block
+#pragma unroll 1
+            for (int s = 0; s < HZ; ++s) {
+                SV Rt = ws + (L::o_Rt + NU * NU * s);
+                if (NF > 1)
+                    for (int e = 0; e < NU * NU; ++e) Rt[e] = 0.0;
+                for (int li = 0; li < NF; ++li) {
+                    const int j = s * NF + li;
+#pragma unroll 1
+                    for (int a = 0; a < LB; ++a)
+#pragma unroll 1
+                        for (int b = 0; b <= a; ++b) {
+                            double acc = (a == b) ? Rd[fo[j]][a] : 0.0;
+#pragma unroll 1
+                            for (int k = 0; k < mb; ++k) acc += Cb[k * LB + a] * Cb[k * LB + b] * r_d[j * mb + k];
+                            Rt[(li * LB + a) * NU + li * LB + b] = acc;
+                            Rt[(li * LB + b) * NU + li * LB + a] = acc;
+                        }
+                }
+            }
+            gather(r_w, rdv, 1.0, xv);
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) xv[i] = -xv[i];  // -rd - C' w
+            if (!factor()) {
+                status = 2;
+                break;
+            }
+            solve(xv);
+            double ratio = 0.0;
+            part = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < S; ++j)
+#pragma unroll 1
+                for (int k = 0; k < mb; ++k) {
+                    const int r = j * mb + k;
+                    const double dsa = -r_p[r] - cdot(k, xv + j * LB);
+                    const double dla = -r_l[r] - r_d[r] * dsa;
+                    ratio = fmax(ratio, fmax(-dsa / r_s[r], -dla / r_l[r]));
+                    r_c[r] = dsa * dla;
+                    part += dsa * dla;
+                }
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) duv[i] = xv[i];
+            const double a_aff = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+            const double mu_aff = mu * (1.0 - a_aff) + a_aff * a_aff * part / (double)m;
+            double sigma = mu_aff / mu;
+            sigma = sigma * sigma * sigma;
+            const double tgt = sigma * mu;
+#pragma unroll 1
+            for (int r = 0; r < m; ++r) r_c[r] = (r_c[r] - tgt) / r_s[r];
+            gather(r_c, xv, 0.0, xv);
+            solve(xv);
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) duv[i] += xv[i];
+            ratio = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < S; ++j)
+#pragma unroll 1
+                for (int k = 0; k < mb; ++k) {
+                    const int r = j * mb + k;
+                    const double ds = -r_p[r] - cdot(k, duv + j * LB);
+                    const double dl = -r_l[r] - r_c[r] - r_d[r] * ds;
+                    ratio = fmax(ratio, fmax(-ds / r_s[r], -dl / r_l[r]));
+                    r_p[r] = ds;
+                    r_c[r] = dl;
+                }
+            double a2 = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+            if (!isfinite(ratio)) {
+                status = 2;
+                break;
+            }
+            if (p.gondzio && a2 < p.gondzio_below) {
+                const double at = fmin(1.0, 1.5 * a2 + 0.1);
+#pragma unroll 1
+                for (int r = 0; r < m; ++r) {
+                    const double v = (r_s[r] + at * r_p[r]) * (r_l[r] + at * r_c[r]);
+                    double vt = fmin(fmax(v, 0.1 * tgt), 10.0 * tgt) - v;
+                    vt = fmax(vt, -10.0 * tgt);
+                    r_w[r] = -vt / r_s[r];
+                }
+                gather(r_w, xv, 0.0, xv);
+                solve(xv);
+                ratio = 0.0;
+#pragma unroll 1
+                for (int j = 0; j < S; ++j)
+#pragma unroll 1
+                    for (int k = 0; k < mb; ++k) {
+                        const int r = j * mb + k;
+                        const double cx = cdot(k, xv + j * LB);
+                        const double ds = r_p[r] - cx;
+                        const double dl = r_c[r] + r_d[r] * cx - r_w[r];
+                        ratio = fmax(ratio, fmax(-ds / r_s[r], -dl / r_l[r]));
+                    }
+                const double a3 = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+                if (isfinite(ratio) && a3 > a2) {
+                    a2 = a3;
+#pragma unroll 1
+                    for (int j = 0; j < S; ++j)
+#pragma unroll 1
+                        for (int k = 0; k < mb; ++k) {
+                            const int r = j * mb + k;
+                            const double cx = cdot(k, xv + j * LB);
+                            r_p[r] -= cx;
+                            r_c[r] += r_d[r] * cx - r_w[r];
+                        }
+#pragma unroll 1
+                    for (int i = 0; i < N; ++i) duv[i] += xv[i];
+                }
+            }
+            const double alpha = (it > 14 ? 0.9 : p.step_frac) * a2;
+#pragma unroll 1
+            for (int r = 0; r < m; ++r) {
+                r_s[r] += alpha * r_p[r];
+                r_l[r] += alpha * r_c[r];
+            }
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) uv[i] += alpha * duv[i], rdv[i] *= (1.0 - alpha);
+            rdmax *= (1.0 - alpha);
+        }
+
+        // ---- 3. active-set polish + certificate (one attempt; anything else goes to the warp-per-robot kernels) ----
+        int amask[S], bdim[S];
+        bool polished = false;
+        if (status == 0) {
+            // diag(Hc) from the uncontrolled cost-to-go
+            {
+                SV P = ws + L::o_P;
+#pragma unroll 1
+                for (int e = 0; e < 144; ++e) P[e] = 0.0;
+#pragma unroll
+                for (int a = 0; a < 12; ++a) P[a * 13] = p.Q[a];
+#pragma unroll 1
+                for (int i = HZ - 1; i >= 0; --i) {
+                    SV B = ws + (L::o_B0 + 6 * NU * i);
+#pragma unroll 1
+                    for (int c = 0; c < NU; ++c) {
+                        double b[6], acc = Rd[fo[i * NF + c / LB]][c % LB];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) b[k] = B[k * NU + c];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k)
+#pragma unroll
+                            for (int k2 = 0; k2 < 6; ++k2) acc += b[k] * P[(6 + k) * 12 + 6 + k2] * b[k2];
+                        hd[i * NU + c] = acc;
+                    }
+                    if (i == 0) break;
+                    congruence(P, ws + (L::o_rinv + 9 * i));
+#pragma unroll
+                    for (int a = 0; a < 12; ++a) P[a * 13] += p.Q[a];
+                }
+            }
+#pragma unroll 1
+            for (int j = 0; j < S; ++j) {
+                int mk = 0;
+#pragma unroll 1
+                for (int k = 0; k < mb; ++k) {
+                    double th = 0.0, aa = 0.0;
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) th += Cb[k * LB + c] * Cb[k * LB + c] * hd[j * LB + c], aa += Cb[k * LB + c] * Cb[k * LB + c];
+                    if (r_l[j * mb + k] * fmax(aa * aa, 1e-300) > th * r_s[j * mb + k]) mk |= 1 << k;
+                }
+                amask[j] = mk;
+            }
+            status = 1;
+#pragma unroll 1
+            for (int round = 0; round < p.polish_rounds; ++round) {
+                bool bad_blk = false;
+#pragma unroll 1
+                for (int j = 0; j < S; ++j) {
+                    double pl[LB], Nl[E];
+                    int dim = 0;
+                    if (!block_nullspace<LB>(Cb, rb, mb, (unsigned)amask[j], pl, Nl, &dim)) bad_blk = true;
+                    bdim[j] = dim;
+                    for (int c = 0; c < LB; ++c) ppv[j * LB + c] = pl[c];
+                    for (int e = 0; e < E; ++e) Nn[j * E + e] = Nl[e];
+                }
+                if (bad_blk) break;
+                grad(ppv, tvp, nullptr);
+                // reduced LQR: inputs w_b, maps B_b N_b, weights N_b' R N_b (+ I on the padding)
+#pragma unroll 1
+                for (int s = 0; s < HZ; ++s) {
+                    SV Rt = ws + (L::o_Rt + NU * NU * s), B0 = ws + (L::o_B0 + 6 * NU * s), Bm = ws + (L::o_Bm + 6 * NU * s);
+                    if (NF > 1)
+                        for (int e = 0; e < NU * NU; ++e) Rt[e] = 0.0;
+                    for (int li = 0; li < NF; ++li) {
+                        const int j = s * NF + li, dim = bdim[j];
+                        SV Nj = Nn + j * E;
+#pragma unroll 1
+                        for (int a = 0; a < LB; ++a) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int c = 0; c < LB; ++c) acc += Nj[c * LB + a] * tvp[j * LB + c];
+                            xv[j * LB + a] = (a < dim) ? -acc : 0.0;
+#pragma unroll 1
+                            for (int b = 0; b <= a; ++b) {
+                                double w = 0.0;
+#pragma unroll
+                                for (int c = 0; c < LB; ++c) w += Nj[c * LB + a] * Rd[fo[j]][c] * Nj[c * LB + b];
+                                if (a == b && a >= dim) w = 1.0;
+                                Rt[(li * LB + a) * NU + li * LB + b] = w;
+                                Rt[(li * LB + b) * NU + li * LB + a] = w;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) {
+                                double w = 0.0;
+#pragma unroll
+                                for (int c = 0; c < LB; ++c) w += B0[k * NU + li * LB + c] * Nj[c * LB + a];
+                                Bm[k * NU + li * LB + a] = w;
+                            }
+                        }
+                    }
+                }
+                if (!factor()) break;
+                solve(xv);
+#pragma unroll 1
+                for (int j = 0; j < S; ++j) {
+                    SV Nj = Nn + j * E;
+#pragma unroll 1
+                    for (int c = 0; c < LB; ++c) {
+                        double acc = ppv[j * LB + c];
+#pragma unroll
+                        for (int a = 0; a < LB; ++a) acc += Nj[c * LB + a] * xv[j * LB + a];
+                        upv[j * LB + c] = acc;
+                    }
+                }
+                // primal check: violated inactive rows join the active set
+                bool changed = false;
+#pragma unroll 1
+                for (int j = 0; j < S; ++j)
+#pragma unroll 1
+                    for (int k = 0; k < mb; ++k) {
+                        const double bk = rb[k];
+                        const double viol = cdot(k, upv + j * LB) - bk;
+                        if (viol > 1e-9 * (1.0 + fabs(bk)) && !((amask[j] >> k) & 1)) amask[j] |= 1 << k, changed = true;
+                    }
+                if (changed) continue;
+                // dual check: minus the gradient must be a non-negative combination of the active rows
+                grad(upv, tvp, nullptr);
+                bool fail = false;
+#pragma unroll 1
+                for (int j = 0; j < S; ++j) {
+                    double rneg[LB], lam[L::MBM];
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) rneg[c] = -tvp[j * LB + c];
+                    for (int k = 0; k < mb; ++k) lam[k] = r_l[j * mb + k];
+                    unsigned drop = 0u;
+                    if (block_dual_fast<LB>(Cb, mb, (unsigned)amask[j], lam, rneg, gs)) continue;
+                    if (!block_dual_check<LB>(Cb, mb, (unsigned)amask[j], rneg, gs, &drop)) {
+                        if (drop == 0u) fail = true;
+                        else amask[j] &= ~(int)drop, changed = true;
+                    }
+                }
+                if (fail) break;
+                if (!changed) {
+                    polished = true;
+                    break;
+                }
+            }
+        }
+        if (!polished) {
+            io.status[inst] = 1;
+            io.iters[inst] = it;
+            return;
+        }
+
+        // ---- 4. outputs ----
+        double u0[12];
+        double umax = 0.0;
+        for (int e = 0; e < HZ * 12; ++e) {
+            const int s = e / 12, c12 = e - 12 * s;
+            const int l = (c12 % 6) / 3, comp = (c12 < 6) ? (c12 % 3) : (3 + c12 % 3);
+            const int b = blockOf[2 * s + l];
+            double val = 0.0;
+            if (b >= 0) {
+                val = p.lo6[comp];
+                for (int c = 0; c < LB; ++c)
+                    if (p.comps[c] == comp) val = upv[b * LB + c];
+            }
+            io.controls[(size_t)inst * HZ * 12 + e] = val;
+            umax = fmax(umax, fabs(val));
+            if (s == 0) u0[c12] = val;
+        }
+        const double uscale = fmax(1.0, umax);
+        if (io.states) grad(upv, tvp, io.states + (size_t)inst * HZ * 13);
+        if (io.fric_active) {
+            for (int s = 0; s < HZ; ++s) {
+                const double tol = 1e-6 * uscale;
+                unsigned mask = 0;
+                for (int l = 0; l < 2; ++l) {
+                    const int b = blockOf[2 * s + l];
+                    if (b < 0) continue;
+                    double f[3] = {p.lo6[0], p.lo6[1], p.lo6[2]};
+                    for (int c = 0; c < LB; ++c)
+                        if (p.comps[c] < 3) f[p.comps[c]] = upv[b * LB + c];
+                    if (f[2] <= tol) continue;
+                    const double res[4] = {f[0] - p.mu * f[2], f[1] - p.mu * f[2], -f[0] - p.mu * f[2], -f[1] - p.mu * f[2]};
+                    for (int r = 0; r < 4; ++r)
+                        if (res[r] >= -tol) mask |= 1u << (4 * l + r);
+                }
+                io.fric_active[(size_t)inst * HZ + s] = (uint8_t)mask;
+            }
+        }
+        if (io.do_lowlevel && io.tau) {
+            double q[10], qd[10], pf[6];
+            for (int a = 0; a < 10; ++a) q[a] = io.q[(size_t)inst * 10 + a], qd[a] = io.qd[(size_t)inst * 10 + a];
+            for (int a = 0; a < 6; ++a) pf[a] = io.pf_w[(size_t)inst * 6 + a];
+            for (int leg = 0; leg < 2; ++leg) {
+                double tl[5];
+                lowlevel_leg(p, x_fb, io.t_swing[inst], pf, q, qd, rotn, leg, (double)cont0[leg], u0, tl);
+                for (int c = 0; c < 5; ++c) io.tau[(size_t)inst * 10 + 5 * leg + c] = tl[c];
+            }
+        }
+        if (io.ws_mask)
+            for (int e = 0; e < 2 * HZ; ++e) io.ws_mask[(size_t)inst * 2 * HZ + e] = blockOf[e] >= 0 ? amask[blockOf[e]] : -1;
+        io.status[inst] = 0;
+        io.iters[inst] = it;
+        if (io.resid) io.resid[2 * inst] = 0.0, io.resid[2 * inst + 1] = rdmax;
+    }
+};
+
+#if defined(__CUDACC__) && !defined(BMPC_LANE_HOST_ONLY)
+// One warp = 32 robots of the class's work list at a time (dynamic: a global counter hands out 32-robot slices).
+template <int HZ, int NF, int LB>
+__global__ void __launch_bounds__(128) lane_tick_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
+                                                        const int* __restrict__ work_list, const int* __restrict__ work_count,
+                                                        int* __restrict__ slice_counter, double* __restrict__ wsbase) {
+    using L = LaneL<HZ, NF, LB>;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int count = *work_count;
+    SV ws{wsbase + (size_t)warp * L::total * 32 + lane};
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(slice_counter, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        if (base + lane < count) {
+            LaneSolver<HZ, NF, LB> solver(p, ws);
+            solver.run(io, work_list[base + lane]);
+        }
+        __syncwarp();
+    }
+}
+#endif
+
+}  // namespace bmpc

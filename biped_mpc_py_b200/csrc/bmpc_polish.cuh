@@ -24,7 +24,7 @@ namespace bmpc {
 // is a compile-time constant (no local memory); perm[] maps positions back to components and the
 // first *np positions are the pivots.  A[i][LB] is the transformed right-hand side.
 template <int LB>
-__device__ __forceinline__ void normal_reduce(const double* __restrict__ Cb, int mb, unsigned mask,
+BMPC_HD __forceinline__ void normal_reduce(const double* __restrict__ Cb, int mb, unsigned mask,
                                               const double (&rhs)[LB], double (&A)[LB][LB + 1], int (&perm)[LB],
                                               int& np) {
 #pragma unroll
@@ -103,7 +103,7 @@ __device__ __forceinline__ void normal_reduce(const double* __restrict__ Cb, int
 // p and N are written with run-time component indices, so they should point to shared memory.
 // false if the rows are inconsistent.
 template <int LB>
-__device__ __noinline__ bool block_nullspace(const double* __restrict__ Cb, const double* __restrict__ rb, int mb,
+BMPC_HD __noinline__ bool block_nullspace(const double* __restrict__ Cb, const double* __restrict__ rb, int mb,
                                              unsigned mask, double* __restrict__ p, double* __restrict__ N,
                                              int* __restrict__ dim_out) {
     double rhs[LB];
@@ -153,7 +153,7 @@ __device__ __noinline__ bool block_nullspace(const double* __restrict__ Cb, cons
 // optimal dual face, so y >= 0 whenever the active set is right and strictly complementary.
 // true: y >= 0 and C_A' y = r (certificate holds).  false: undecided, run the exact NNLS check.
 template <int LB>
-__device__ __noinline__ bool block_dual_fast(const double* __restrict__ Cb, int mb, unsigned mask,
+BMPC_HD __noinline__ bool block_dual_fast(const double* __restrict__ Cb, int mb, unsigned mask,
                                              const double* __restrict__ lam, const double* __restrict__ r, double gs) {
     double rho[LB];
 #pragma unroll
@@ -194,7 +194,7 @@ __device__ __noinline__ bool block_dual_fast(const double* __restrict__ Cb, int 
 // below tolerance; otherwise *drop receives the active rows the residual direction moves away
 // from (to be released), possibly 0 (then the polish gives up).
 template <int LB>
-__device__ __noinline__ bool block_dual_check(const double* __restrict__ Cb, int mb, unsigned mask, const double* __restrict__ r,
+BMPC_HD __noinline__ bool block_dual_check(const double* __restrict__ Cb, int mb, unsigned mask, const double* __restrict__ r,
                                  double gs, unsigned* __restrict__ drop) {
     double A[MAXROWS][LB];
     int rows[MAXROWS];
