@@ -12,6 +12,7 @@
 #include <string>
 
 #include "../../include/biped_mpc_b200.h"
+#include "bmpc_lane.cuh"
 #include "bmpc_presolve.h"
 #include "bmpc_rollout.cuh"
 #include "bmpc_small.cuh"
@@ -35,6 +36,15 @@ int fail(const std::string& msg) {
 
 typedef void (*TickKernel)(const DevParams, const IoPtrs, const int*, const int*, double*);
 
+typedef void (*LaneKernel)(const DevParams, const IoPtrs, const int*, const int*, int*, double*);
+
+// lane-per-robot front end of one class (bmpc_lane.cuh): what it certifies is done, the rest goes to the class's Variant
+struct LaneVariant {
+    LaneKernel fn = nullptr;
+    int grid = 0;
+    double* d_ws = nullptr;  // [warps][total][32] lane-interleaved work arrays
+};
+
 struct Variant {
     TickKernel fn = nullptr;
     size_t smem = 0;
@@ -55,9 +65,11 @@ struct bmpc_handle {
     DevParams dp;
     Variant bucket[2];
     Variant lowlat;           // walking class for small batches: 128 threads per robot (latency, not throughput), or empty
+    LaneVariant lane[2];      // h = 10, LB = 5: lane-per-robot front end per class (batches >= lane_min), or empty
+    int lane_min = 0;
     Variant fallback;         // dense re-solve of instances the stage-wise class-1 kernel did not certify (h = 30), or empty
-    int* d_lists = nullptr;   // [3][max_batch]: two classes + the fallback list
-    int* d_counts = nullptr;  // [3]
+    int* d_lists = nullptr;   // [5][max_batch]: two classes, the h = 30 fallback list, the two lane-residual lists
+    int* d_counts = nullptr;  // [16]: list count i has its dynamic work counter at i + 3 (lists 0-2 and 6-7); 12, 13 lane slice counters
     int64_t launches = 0;
     // closed-loop rollout workspace (allocated on the first bmpc_rollout call, max_batch sized)
     struct {
@@ -102,6 +114,18 @@ int setup_variant(Variant& v, int num_sms, int mb) {
     return 0;
 }
 
+template <int HZ, int NF, int LB>
+int setup_lane(LaneVariant& v, int num_sms, int ctas_per_sm) {
+    v.fn = lane_tick_kernel<HZ, NF, LB>;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, 128, 0));
+    if (per_sm < 1) return fail("lane kernel does not fit on an SM");
+    if (ctas_per_sm > 0) per_sm = std::min(per_sm, ctas_per_sm);
+    v.grid = per_sm * num_sms;
+    CUDA_TRY(cudaMalloc(&v.d_ws, sizeof(double) * (size_t)LaneL<HZ, NF, LB>::total * 32 * 4 * (size_t)v.grid));
+    return 0;
+}
+
 int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n > h->max_batch) return fail("batch larger than max_batch given to bmpc_create");
@@ -114,7 +138,7 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     }
     io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
                  (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
-    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 6 * sizeof(int), st));  // three list counts + three dynamic work counters
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 16 * sizeof(int), st));  // list counts + dynamic work counters
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
@@ -125,8 +149,18 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         const Variant& v = (b == 0 && h->lowlat.fn && n <= 8) ? h->lowlat : h->bucket[b];
         // persistent thread groups: as many as fit on the device, each strides over its bucket's work list
         const int grid = (std::min(n, v.resident) + v.per_cta - 1) / v.per_cta;
-        v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b,
-                                               v.d_scratch);
+        const int* list = h->d_lists + (size_t)b * h->max_batch;
+        const int* cnt = h->d_counts + b;
+        if (h->lane[b].fn && n >= h->lane_min && !io.warm) {
+            // throughput batches: one THREAD per robot first (32 robots share every instruction); robots it does not
+            // certify (status 1) are collected and solved by the warp-per-robot kernel below
+            int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
+            h->lane[b].fn<<<h->lane[b].grid, 128, 0, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b, h->lane[b].d_ws);
+            collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b);
+            list = rlist, cnt = h->d_counts + 6 + b;
+            h->launches += 2;
+        }
+        v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, list, cnt, v.d_scratch);
         if (b == 1 && h->fallback.fn) {
             // instances of EITHER class that the stage-wise kernels did not certify: dense re-solve (handles any S <= 2h)
             const Variant& f = h->fallback;
@@ -222,6 +256,16 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         else
 #endif
             if (!rc) rc = setup_variant<10, 20, 5, 128, 1>(h->bucket[1], sms, mb);  // standing: one 128-thread CTA per robot
+        // Lane-per-robot front end (bmpc_lane.cuh): EXPERIMENT, off unless BMPC_LANE=1.  Correct (every robot certified, GPU
+        // parity tests green with it on) but slower than the warp-per-robot kernels in its first form: its per-robot work
+        // arrays (30 KB) live in global memory and the kernel is L1/L2-traffic bound (profiles/r1_summary.md, "lane").
+        const char* ela = getenv("BMPC_LANE");
+        if (!rc && ela && atoi(ela) != 0) {
+            const char* elm = getenv("BMPC_LANE_MIN");
+            h->lane_min = elm ? atoi(elm) : 2048;
+            const char* elc = getenv("BMPC_LANE_CTAS");  // CTAs (4 warps = 128 robots each) per SM
+            rc = setup_lane<10, 1, 5>(h->lane[0], sms, elc ? atoi(elc) : 0) || setup_lane<10, 2, 5>(h->lane[1], sms, elc ? atoi(elc) : 0);
+        }
         const char* ell = getenv("BMPC_LOWLAT");  // 0 disables the low-latency walking variant for batches <= 8
         if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, sms, mb);
     } else {
@@ -231,8 +275,8 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         delete h;
         return 1;
     }
-    e = cudaMalloc(&h->d_lists, sizeof(int) * 3 * (size_t)max_batch);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 6);
+    e = cudaMalloc(&h->d_lists, sizeof(int) * 5 * (size_t)max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 16);
     if (e != cudaSuccess) {
         cudaFree(h->d_lists);
         delete h;
@@ -250,6 +294,7 @@ int bmpc_destroy(bmpc_handle* h) {
     for (int b = 0; b < 2; ++b) cudaFree(h->bucket[b].d_scratch);
     cudaFree(h->fallback.d_scratch);
     cudaFree(h->lowlat.d_scratch);
+    cudaFree(h->lane[0].d_ws), cudaFree(h->lane[1].d_ws);
     cudaFree(h->ro.contact), cudaFree(h->ro.phase_k), cudaFree(h->ro.t_swing), cudaFree(h->ro.controls);
     cudaFree(h->ro.tau), cudaFree(h->ro.status), cudaFree(h->ro.iters), cudaFree(h->ro.ws_mask);
     for (int i = 0; i < 4; ++i)

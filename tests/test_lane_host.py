@@ -1,0 +1,98 @@
+"""The lane-per-robot solver source (biped_mpc_py_b200/csrc/bmpc_lane.cuh: one thread per robot, stage-wise Riccati
+interior point + active-set polish + KKT certificate, sharing bmpc_polish.cuh with the warp-per-robot kernel) compiled
+for the HOST by tests/lane_host.cu and checked against the reference-generated fixtures and the oracle.
+
+This runs the product's device source on the CPU purely as a unit test of its arithmetic (no GPU here); the product
+itself never loads this library (biped_mpc_py_b200 has no CPU path)."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, variant_params
+
+SRC = os.path.join(ROOT, "tests", "lane_host.cu")
+OUT = os.path.join(ROOT, "tests", "_build", "liblane_host.so")
+DEPS = [SRC] + [os.path.join(ROOT, "biped_mpc_py_b200", "csrc", f)
+                for f in ("bmpc_lane.cuh", "bmpc_polish.cuh", "bmpc_kernels.cuh", "bmpc_presolve.h")]
+
+
+@pytest.fixture(scope="module")
+def lane_lib():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+        if not os.path.exists(nvcc):
+            pytest.skip("nvcc not available to build the host test library")
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-DBMPC_LANE_HOST_ONLY", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC], check=True)
+    return ctypes.CDLL(OUT)
+
+
+def _run(lib, mpc, biped, x_fb, t, foot, contact, q, qd, pf_w):
+    from biped_mpc_py_b200.gait import gait_phase
+    from biped_mpc_py_b200.params import pack_params
+    n = x_fb.shape[0]
+    P = pack_params(mpc, biped)
+    c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
+    x_fb, t, foot, q, qd, pf_w = c(x_fb), c(t), c(foot), c(q), c(qd), c(pf_w)
+    contact = c(contact, np.uint8)
+    phase_k = c(gait_phase(t, mpc) % int(mpc.h), np.int32)
+    out = dict(controls=np.zeros((n, 10, 12)), states=np.zeros((n, 10, 13)), tau=np.zeros((n, 10)),
+               status=np.full(n, -7, np.int32), iters=np.zeros(n, np.int32), fric=np.zeros((n, 10), np.uint8),
+               resid=np.zeros((n, 2)), ws_mask=np.zeros((n, 20), np.int32))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.lane_host_tick(ctypes.byref(P), n, p(x_fb), p(phase_k), p(t), p(foot), p(contact), p(q), p(qd), p(pf_w),
+                            p(out["controls"]), p(out["states"]), p(out["tau"]), p(out["status"]), p(out["iters"]),
+                            p(out["fric"]), p(out["resid"]), p(out["ws_mask"]))
+    assert rc == 0
+    return out
+
+
+def test_lane_solver_matches_reference_fixtures(lane_lib, golden):
+    """Fixture cases generated from the real reference module (variants with one pinned component, h = 10)."""
+    g = golden
+    checked = 0
+    for variant in (0, 1):
+        idx = np.nonzero(g["variant"] == variant)[0]
+        mpc, biped = variant_params(variant)
+        out = _run(lane_lib, mpc, biped, g["x_fb"][idx], g["t"][idx], g["pf_w"][idx], g["contact"][idx], g["q"][idx],
+                   g["qd"][idx], g["pf_w"][idx])
+        per_stage = g["contact"][idx].astype(int).sum(axis=2)
+        uniform = (per_stage == per_stage[:, :1]).all(axis=1) & (per_stage[:, 0] > 0)
+        # every robot with the same number (1 or 2) of stance feet in every stage is this path's and must certify
+        assert (out["status"][uniform] == 0).all(), out["status"]
+        assert (out["status"][~uniform] == 1).all()
+        for j, c in enumerate(idx):
+            if out["status"][j] != 0:
+                continue
+            scale = max(1.0, np.abs(g["controls"][c]).max())
+            assert np.abs(out["controls"][j] - g["controls"][c]).max() / scale <= 1e-5, c   # north_star: 1e-4 relative
+            assert np.abs(out["tau"][j] - g["tau"][c]).max() <= 1e-4, c                     # north_star: 1e-4 N*m
+            assert np.abs(out["states"][j] - g["states"][c]).max() <= 1e-6, c
+            checked += 1
+    assert checked >= 30
+
+
+def test_lane_solver_matches_oracle_on_synthetic(lane_lib):
+    from biped_mpc_py_b200 import synth
+    from oracle import reference_mpc as rm
+    mpc, biped = rm.MPCParams(), rm.BipedParams()
+    n = 512
+    b = synth.make_batch(n, shard_index=11, mpc=mpc, biped=biped)
+    out = _run(lane_lib, mpc, biped, b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+    assert (out["status"] == 0).all(), np.bincount(out["status"])
+    assert 7.5 < out["iters"].mean() < 10.5
+    for i in range(12):
+        states, controls = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, biped, b["contact"][i])
+        tau = rm.lowLevelControl(b["x_fb"][i], float(b["t"][i]), b["pf_w"][i].reshape(6, 1), b["q"][i], b["qd"][i], mpc, biped,
+                                 b["contact"][i], controls[0].reshape(-1, 1)).reshape(-1)
+        scale = max(1.0, np.abs(controls).max())
+        assert np.abs(out["controls"][i] - controls).max() / scale <= 1e-5
+        assert np.abs(out["tau"][i] - tau).max() <= 1e-4
+        assert np.abs(out["states"][i] - states).max() <= 1e-6
+        mask = [rm.active_friction_rows(controls[s], b["contact"][i][s], biped.mu, scale) for s in range(10)]
+        assert (out["fric"][i] == np.array(mask, dtype=np.uint8)).all()
