@@ -290,3 +290,35 @@ def test_mixed_contact_patterns(torch_cuda):
     du = np.abs(out["controls"] - U).reshape(16, -1).max(axis=1) / scale
     assert du.max() <= U_RTOL_TIGHT and np.abs(out["tau"] - T).max() <= TAU_ATOL_TIGHT, (du.max(),)
     solver.close()
+
+
+def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
+    """The experimental lane-per-robot kernels (BMPC_LANE=1, csrc/bmpc_lane.cuh; one thread per robot, everything they do
+    not certify falls through to the warp-per-robot kernels) must return the same certified optimum as the default path:
+    synthetic batch + arbitrary contact schedules (those are not the lane path's and exercise the fall-through)."""
+    from biped_mpc_py_b200 import synth
+    n = 2048
+    mpc, biped = variant_params(0)
+    b = synth.make_batch(n, shard_index=9, mpc=mpc, biped=biped)
+    rng = np.random.default_rng(9)
+    b["contact"][:64] = (rng.uniform(size=(64, 10, 2)) < 0.6).astype(np.uint8)
+    b["x_fb"][64, 1] = np.nan  # bad input must still be flagged through the fall-through
+    args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+    ref_solver, _, _ = _solver(0, max_batch=n)
+    ref = ref_solver.step_host(*args, want_states=True)
+    ref_solver.close()
+    monkeypatch.setenv("BMPC_LANE", "1")
+    monkeypatch.setenv("BMPC_LANE_MIN", "1")
+    lane_solver, _, _ = _solver(0, max_batch=n)
+    launches0 = lane_solver.launch_count
+    out = lane_solver.step_host(*args, want_states=True)
+    assert lane_solver.launch_count - launches0 == 7  # classify + 2 x (lane, collect, warp-per-robot)
+    lane_solver.close()
+    assert (out["status"] == ref["status"]).all() and out["status"][64] == 3 and (np.delete(out["status"], 64) == 0).all()
+    ok = out["status"] == 0
+    scale = np.maximum(1.0, np.abs(ref["controls"]).reshape(n, -1).max(axis=1))
+    du = np.abs(out["controls"] - ref["controls"]).reshape(n, -1).max(axis=1) / scale
+    assert du[ok].max() <= 1e-8, du[ok].max()
+    assert np.abs(out["tau"] - ref["tau"])[ok].max() <= 1e-7
+    assert np.abs(out["states"] - ref["states"])[ok].max() <= 1e-8
+    assert (out["fric_active"] == ref["fric_active"])[ok].all()
