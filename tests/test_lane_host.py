@@ -96,3 +96,39 @@ def test_lane_solver_matches_oracle_on_synthetic(lane_lib):
         assert np.abs(out["states"][i] - states).max() <= 1e-6
         mask = [rm.active_friction_rows(controls[s], b["contact"][i][s], biped.mu, scale) for s in range(10)]
         assert (out["fric"][i] == np.array(mask, dtype=np.uint8)).all()
+
+
+def test_lane_solver_randomised_parameter_sets(lane_lib):
+    """Friction coefficient, mass, limits, weights and commanded velocities drawn at random (one pinned moment component,
+    as in the reference): every robot this path accepts must certify and agree with the oracle; parameter sets with more
+    than 12 surviving inequality rows per block are not this path's (status 1 = handed to the warp-per-robot kernels)."""
+    from biped_mpc_py_b200 import synth
+    from oracle import reference_mpc as rm
+    rng = np.random.default_rng(123)
+    accepted = 0
+    for trial in range(6):
+        mpc, biped = rm.MPCParams(), rm.BipedParams()
+        biped.mu = float(rng.uniform(0.3, 0.9))
+        biped.m = float(rng.uniform(9, 20))
+        fm = float(rng.uniform(200, 600))
+        biped.f_max = np.array([[fm], [fm], [float(rng.uniform(250, 600))]])
+        if trial % 2:
+            biped.f_min = np.array([[-fm], [-fm], [0.0]])
+        biped.tau_max = np.array([[0.0], [float(rng.uniform(20, 80))], [float(rng.uniform(10, 40))]])
+        biped.tau_min = -biped.tau_max
+        mpc.x_cmd = np.array([0, 0, 0, 0, 0, 0.55, 0, 0, float(rng.uniform(-0.3, 0.3)) * (trial % 3 == 0),
+                              float(rng.uniform(-0.4, 0.4)), float(rng.uniform(-0.2, 0.2)), 0])
+        mpc.Q = mpc.Q * np.exp(rng.normal(0, 0.5, 13))
+        mpc.R = mpc.R * np.exp(rng.normal(0, 1.0, 12))
+        n = 32
+        b = synth.make_batch(n, shard_index=100 + trial, mpc=mpc, biped=biped)
+        out = _run(lane_lib, mpc, biped, b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+        if (out["iters"] == 0).all():
+            assert (out["status"] == 1).all()   # whole parameter set declined (row count), nothing half-solved
+            continue
+        assert (out["status"] == 0).all(), (trial, np.bincount(out["status"]))
+        accepted += 1
+        for i in (0, n - 1):
+            _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, biped, b["contact"][i])
+            assert np.abs(out["controls"][i] - u).max() / max(1.0, np.abs(u).max()) <= 1e-5, (trial, i)
+    assert accepted >= 4
