@@ -264,7 +264,8 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
             const char* elm = getenv("BMPC_LANE_MIN");
             h->lane_min = elm ? atoi(elm) : 2048;
             const char* elc = getenv("BMPC_LANE_CTAS");  // CTAs (4 warps = 128 robots each) per SM
-            rc = setup_lane<10, 1, 5>(h->lane[0], sms, elc ? atoi(elc) : 0) || setup_lane<10, 2, 5>(h->lane[1], sms, elc ? atoi(elc) : 0);
+            rc = setup_lane<10, 1, 5>(h->lane[0], sms, elc ? atoi(elc) : 0);               // BMPC_LANE=1: walking class only
+            if (!rc && atoi(ela) >= 2) rc = setup_lane<10, 2, 5>(h->lane[1], sms, elc ? atoi(elc) : 0);  // 2: both classes
         }
         const char* ell = getenv("BMPC_LOWLAT");  // 0 disables the low-latency walking variant for batches <= 8
         if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, sms, mb);

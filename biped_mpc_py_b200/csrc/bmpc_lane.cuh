@@ -153,6 +153,7 @@ struct LaneSolver {
 
     // ---- backward Riccati sweep: factors  blockdiag(Rt) + B' (state cost) B  in stage-wise form --------------------
     BMPC_HD bool factor() {
+        if constexpr (NF == 1 && LB == 5) return factor1();
         SV P = ws + L::o_P, PB = ws + L::o_PB, F = ws + L::o_F, G = ws + L::o_G;
 #pragma unroll 1
         for (int e = 0; e < 144; ++e) P[e] = 0.0;
@@ -258,6 +259,10 @@ struct LaneSolver {
 
     // x <- inv(M) x  with the factor of the last factor() call
     BMPC_HD void solve(SV x) {
+        if constexpr (NF == 1 && LB == 5) {
+            solve1(x);
+            return;
+        }
         double pv[12];
 #pragma unroll
         for (int a = 0; a < 12; ++a) pv[a] = 0.0;
@@ -326,6 +331,238 @@ struct LaneSolver {
         }
     }
 
+
+    // ---- NF == 1 (walking class): register-blocked stage sweep; cost-to-go kept as a packed lower triangle (78) ----
+    // Per stage the only global traffic is P (read for P B, the congruence and the rank-NU update), B, Rt, and the factor
+    // pieces the solves need:  Y = inv(L) F  (NU x 12) and L  (G = L L').  K = inv(L') Y is never formed:
+    // K z = inv(L') (Y z),  K' g = Y' (inv(L) g),  F' inv(G) F = Y' Y.
+    static BMPC_HD __forceinline__ constexpr int pk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+
+    // P <- A' P A on the packed triangle.  A = [I D; 0 I], D = dt [Rinv 0; 0 I]:  P21 += D' P11,  P22 += D' P12new + P21old D
+    BMPC_HD void congruence_pk(SV P, SV ri) {
+        double r9[9], p11[21], o21[6][6], n21[6][6];
+#pragma unroll
+        for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
+#pragma unroll
+        for (int e = 0; e < 21; ++e) p11[e] = P[e];
+#pragma unroll
+        for (int kp = 0; kp < 6; ++kp)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) o21[kp][c] = P[pk(6 + kp, c)];
+#pragma unroll
+        for (int kp = 0; kp < 3; ++kp)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                n21[kp][c] = o21[kp][c] + r9[kp] * p11[pk(0, c)] + r9[3 + kp] * p11[pk(1, c)] + r9[6 + kp] * p11[pk(2, c)];
+                n21[3 + kp][c] = o21[3 + kp][c] + dt * p11[pk(3 + kp, c)];
+            }
+#pragma unroll
+        for (int kp = 0; kp < 6; ++kp)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) P[pk(6 + kp, c)] = n21[kp][c];
+#pragma unroll
+        for (int kp = 0; kp < 6; ++kp)
+#pragma unroll
+            for (int k = 0; k <= kp; ++k) {
+                double t1, t2;
+                if (kp < 3) t1 = r9[kp] * n21[k][0] + r9[3 + kp] * n21[k][1] + r9[6 + kp] * n21[k][2];
+                else t1 = dt * n21[k][kp];
+                if (k < 3) t2 = o21[kp][0] * r9[k] + o21[kp][1] * r9[3 + k] + o21[kp][2] * r9[6 + k];
+                else t2 = dt * o21[kp][k];
+                P[pk(6 + kp, 6 + k)] += t1 + t2;
+            }
+    }
+
+    BMPC_HD bool factor1() {
+        static_assert(LB == 5, "register-blocked sweep is written for 5 free components per block");
+        SV P = ws + L::o_P;
+#pragma unroll 1
+        for (int e = 0; e < 78; ++e) P[e] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 12; ++a) P[pk(a, a)] = p.Q[a];
+#pragma unroll 1
+        for (int i = HZ - 1; i >= 0; --i) {
+            SV Bv = ws + (L::o_Bm + 30 * i), Rt = ws + (L::o_Rt + 25 * i), ri = ws + (L::o_rinv + 9 * i);
+            SV Y = ws + (L::o_K + 60 * i), Lc = ws + (L::o_Lc + 25 * i);
+            double B[6][5], lo[6][5], hi[6][5], Lr[5][5];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) B[k][c] = Bv[k * 5 + c];
+#pragma unroll
+            for (int r = 0; r < 12; ++r) {
+                double pr[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) pr[k] = P[pk(r, 6 + k)];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc += pr[k] * B[k][c];
+                    if (r < 6) hi[r][c] = acc;
+                    else lo[r - 6][c] = acc;
+                }
+            }
+            // G = Rt + B' PB[6:12], Cholesky in registers (reciprocal diagonal)
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+#pragma unroll
+                for (int a = j; a < 5; ++a) {
+                    double v = Rt[a * 5 + j];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) v += B[k][a] * lo[k][j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) v -= Lr[a][k] * Lr[j][k];
+                    if (a == j) {
+                        ok = ok && (v > 0.0) && (v < 1e300);
+                        Lr[j][j] = 1.0 / sqrt(v);
+                    } else {
+                        Lr[a][j] = v * Lr[j][j];
+                    }
+                }
+            }
+            if (!ok) return false;
+            // F = PB' A in place (columns 6..11 live in lo), then Y = inv(L) F column by column
+            {
+                double r9[9];
+#pragma unroll
+                for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        lo[k][c] += hi[0][c] * r9[k] + hi[1][c] * r9[3 + k] + hi[2][c] * r9[6 + k];
+                        lo[3 + k][c] += dt * hi[3 + k][c];
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    double vh = hi[j][a], vl = lo[j][a];
+#pragma unroll
+                    for (int k = 0; k < a; ++k) vh -= Lr[a][k] * hi[j][k], vl -= Lr[a][k] * lo[j][k];
+                    hi[j][a] = vh * Lr[a][a];
+                    lo[j][a] = vl * Lr[a][a];
+                }
+#pragma unroll
+                for (int a = 0; a < 5; ++a) Y[a * 12 + j] = hi[j][a], Y[a * 12 + 6 + j] = lo[j][a];
+            }
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+                for (int k = 0; k <= a; ++k) Lc[a * 5 + k] = Lr[a][k];
+            if (i == 0) break;
+            // P <- Q + A' P A - Y' Y
+            congruence_pk(P, ri);
+            {
+                double Yr[5][12];
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) Yr[a][j] = Y[a * 12 + j];
+#pragma unroll
+                for (int r = 0; r < 12; ++r)
+#pragma unroll
+                    for (int c = 0; c <= r; ++c) {
+                        double acc = P[pk(r, c)];
+#pragma unroll
+                        for (int a = 0; a < 5; ++a) acc -= Yr[a][r] * Yr[a][c];
+                        if (r == c) acc += p.Q[r];
+                        P[pk(r, c)] = acc;
+                    }
+            }
+        }
+        return true;
+    }
+
+    BMPC_HD void solve1(SV x) {
+        double pv[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) pv[a] = 0.0;
+#pragma unroll 1
+        for (int i = HZ - 1; i >= 0; --i) {
+            SV Bv = ws + (L::o_Bm + 30 * i), ri = ws + (L::o_rinv + 9 * i), Y = ws + (L::o_K + 60 * i), Lc = ws + (L::o_Lc + 25 * i),
+               xi = x + 5 * i;
+            double w[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                double g = -xi[c];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) g += Bv[k * 5 + c] * pv[6 + k];
+#pragma unroll
+                for (int k = 0; k < c; ++k) g -= Lc[c * 5 + k] * w[k];
+                w[c] = g * Lc[c * 5 + c];
+                xi[c] = w[c];
+            }
+            double np[12];
+#pragma unroll
+            for (int a = 0; a < 12; ++a) np[a] = pv[a];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                np[6 + k] += dt * (ri[k] * pv[0] + ri[3 + k] * pv[1] + ri[6 + k] * pv[2]);
+                np[9 + k] += dt * pv[3 + k];
+            }
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+                for (int j = 0; j < 12; ++j) np[j] -= Y[a * 12 + j] * w[a];
+#pragma unroll
+            for (int a = 0; a < 12; ++a) pv[a] = np[a];
+        }
+        double z[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) z[a] = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < HZ; ++i) {
+            SV Bv = ws + (L::o_Bm + 30 * i), ri = ws + (L::o_rinv + 9 * i), Y = ws + (L::o_K + 60 * i), Lc = ws + (L::o_Lc + 25 * i),
+               xi = x + 5 * i;
+            double t[5], xs[5];
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                double v = xi[a];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) v += Y[a * 12 + j] * z[j];
+                t[a] = v;
+            }
+#pragma unroll
+            for (int a = 4; a >= 0; --a) {
+                double v = t[a];
+#pragma unroll
+                for (int k = a + 1; k < 5; ++k) v -= Lc[k * 5 + a] * xs[k];
+                xs[a] = v * Lc[a * 5 + a];
+            }
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                xs[a] = -xs[a];
+                xi[a] = xs[a];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc[k] += Bv[k * 5 + a] * xs[a];
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                z[a] += dt * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
+                z[3 + a] += dt * z[9 + a];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) z[6 + k] += acc[k];
+        }
+    }
+
+    // -dv / v in FP32: only a step LENGTH, cut by step_frac afterwards (same as the warp-per-robot kernel); NaN/Inf propagate
+    static BMPC_HD __forceinline__ float sratio(double dv, double v) { return -(float)dv / (float)v; }
+    BMPC_HD __forceinline__ void crow(int k, double (&cb)[LB]) const {
+#pragma unroll
+        for (int c = 0; c < LB; ++c) cb[c] = Cb[k * LB + c];
+    }
+    BMPC_HD __forceinline__ double cdotr(int k, const double (&v)[LB]) const {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < LB; ++c) acc += Cb[k * LB + c] * v[c];
+        return acc;
+    }
     BMPC_HD __forceinline__ double cdot(int k, SV v) const {
         double acc = 0.0;
 #pragma unroll
@@ -342,8 +579,10 @@ struct LaneSolver {
 #pragma unroll 1
             for (int k = 0; k < mb; ++k) {
                 const double wk = w[j * mb + k];
+                double cb[LB];
+                crow(k, cb);
 #pragma unroll
-                for (int c = 0; c < LB; ++c) acc[c] += Cb[k * LB + c] * wk;
+                for (int c = 0; c < LB; ++c) acc[c] += cb[c] * wk;
             }
 #pragma unroll
             for (int c = 0; c < LB; ++c) out[j * LB + c] = (bscale != 0.0 ? bscale * base[j * LB + c] : 0.0) + acc[c];
@@ -565,17 +804,21 @@ struct LaneSolver {
             ++it;
             part = 0.0;
 #pragma unroll 1
-            for (int j = 0; j < S; ++j)
+            for (int j = 0; j < S; ++j) {
+                double vb[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) vb[c] = uv[j * LB + c];
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
                     const double s = r_s[r], l = r_l[r];
-                    const double d = l / s, rp = cdot(k, uv + j * LB) + s - rb[k];
+                    const double d = l / s, rp = cdotr(k, vb) + s - rb[k];
                     r_d[r] = d;
                     r_p[r] = rp;
                     r_w[r] = d * rp - l;
                     part += s * l;
                 }
+            }
             if (!rd_fresh) {
                 grad(uv, tvp, nullptr);
                 gather(r_l, tvp, 1.0, rdv);
@@ -597,15 +840,27 @@ struct LaneSolver {
                     for (int e = 0; e < NU * NU; ++e) Rt[e] = 0.0;
                 for (int li = 0; li < NF; ++li) {
                     const int j = s * NF + li;
-#pragma unroll 1
+                    double acc[LB * (LB + 1) / 2];
+#pragma unroll
                     for (int a = 0; a < LB; ++a)
+#pragma unroll
+                        for (int b = 0; b <= a; ++b) acc[a * (a + 1) / 2 + b] = (a == b) ? Rd[fo[j]][a] : 0.0;
 #pragma unroll 1
+                    for (int k = 0; k < mb; ++k) {
+                        const double d = r_d[j * mb + k];
+                        double cb[LB];
+                        crow(k, cb);
+#pragma unroll
+                        for (int a = 0; a < LB; ++a)
+#pragma unroll
+                            for (int b = 0; b <= a; ++b) acc[a * (a + 1) / 2 + b] += cb[a] * cb[b] * d;
+                    }
+#pragma unroll
+                    for (int a = 0; a < LB; ++a)
+#pragma unroll
                         for (int b = 0; b <= a; ++b) {
-                            double acc = (a == b) ? Rd[fo[j]][a] : 0.0;
-#pragma unroll 1
-                            for (int k = 0; k < mb; ++k) acc += Cb[k * LB + a] * Cb[k * LB + b] * r_d[j * mb + k];
-                            Rt[(li * LB + a) * NU + li * LB + b] = acc;
-                            Rt[(li * LB + b) * NU + li * LB + a] = acc;
+                            Rt[(li * LB + a) * NU + li * LB + b] = acc[a * (a + 1) / 2 + b];
+                            Rt[(li * LB + b) * NU + li * LB + a] = acc[a * (a + 1) / 2 + b];
                         }
                 }
             }
@@ -617,22 +872,26 @@ struct LaneSolver {
                 break;
             }
             solve(xv);
-            double ratio = 0.0;
+            float ratio = 0.f;
             part = 0.0;
 #pragma unroll 1
-            for (int j = 0; j < S; ++j)
+            for (int j = 0; j < S; ++j) {
+                double vb[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) vb[c] = xv[j * LB + c];
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
-                    const double dsa = -r_p[r] - cdot(k, xv + j * LB);
+                    const double dsa = -r_p[r] - cdotr(k, vb);
                     const double dla = -r_l[r] - r_d[r] * dsa;
-                    ratio = fmax(ratio, fmax(-dsa / r_s[r], -dla / r_l[r]));
+                    ratio = fmaxf(ratio, fmaxf(sratio(dsa, r_s[r]), sratio(dla, r_l[r])));
                     r_c[r] = dsa * dla;
                     part += dsa * dla;
                 }
+            }
 #pragma unroll 1
             for (int i = 0; i < N; ++i) duv[i] = xv[i];
-            const double a_aff = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+            const double a_aff = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
             const double mu_aff = mu * (1.0 - a_aff) + a_aff * a_aff * part / (double)m;
             double sigma = mu_aff / mu;
             sigma = sigma * sigma * sigma;
@@ -643,19 +902,23 @@ struct LaneSolver {
             solve(xv);
 #pragma unroll 1
             for (int i = 0; i < N; ++i) duv[i] += xv[i];
-            ratio = 0.0;
+            ratio = 0.f;
 #pragma unroll 1
-            for (int j = 0; j < S; ++j)
+            for (int j = 0; j < S; ++j) {
+                double vb[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) vb[c] = duv[j * LB + c];
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
-                    const double ds = -r_p[r] - cdot(k, duv + j * LB);
+                    const double ds = -r_p[r] - cdotr(k, vb);
                     const double dl = -r_l[r] - r_c[r] - r_d[r] * ds;
-                    ratio = fmax(ratio, fmax(-ds / r_s[r], -dl / r_l[r]));
+                    ratio = fmaxf(ratio, fmaxf(sratio(ds, r_s[r]), sratio(dl, r_l[r])));
                     r_p[r] = ds;
                     r_c[r] = dl;
                 }
-            double a2 = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+            }
+            double a2 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
             if (!isfinite(ratio)) {
                 status = 2;
                 break;
@@ -671,29 +934,37 @@ struct LaneSolver {
                 }
                 gather(r_w, xv, 0.0, xv);
                 solve(xv);
-                ratio = 0.0;
+                ratio = 0.f;
 #pragma unroll 1
-                for (int j = 0; j < S; ++j)
+                for (int j = 0; j < S; ++j) {
+                    double vb[LB];
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) vb[c] = xv[j * LB + c];
 #pragma unroll 1
                     for (int k = 0; k < mb; ++k) {
                         const int r = j * mb + k;
-                        const double cx = cdot(k, xv + j * LB);
+                        const double cx = cdotr(k, vb);
                         const double ds = r_p[r] - cx;
                         const double dl = r_c[r] + r_d[r] * cx - r_w[r];
-                        ratio = fmax(ratio, fmax(-ds / r_s[r], -dl / r_l[r]));
+                        ratio = fmaxf(ratio, fmaxf(sratio(ds, r_s[r]), sratio(dl, r_l[r])));
                     }
-                const double a3 = (ratio > 1.0) ? 1.0 / ratio : 1.0;
+                }
+                const double a3 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
                 if (isfinite(ratio) && a3 > a2) {
                     a2 = a3;
 #pragma unroll 1
-                    for (int j = 0; j < S; ++j)
+                    for (int j = 0; j < S; ++j) {
+                        double vb[LB];
+#pragma unroll
+                        for (int c = 0; c < LB; ++c) vb[c] = xv[j * LB + c];
 #pragma unroll 1
                         for (int k = 0; k < mb; ++k) {
                             const int r = j * mb + k;
-                            const double cx = cdot(k, xv + j * LB);
+                            const double cx = cdotr(k, vb);
                             r_p[r] -= cx;
                             r_c[r] += r_d[r] * cx - r_w[r];
                         }
+                    }
 #pragma unroll 1
                     for (int i = 0; i < N; ++i) duv[i] += xv[i];
                 }
@@ -817,13 +1088,17 @@ struct LaneSolver {
                 // primal check: violated inactive rows join the active set
                 bool changed = false;
 #pragma unroll 1
-                for (int j = 0; j < S; ++j)
+                for (int j = 0; j < S; ++j) {
+                    double vb[LB];
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) vb[c] = upv[j * LB + c];
 #pragma unroll 1
                     for (int k = 0; k < mb; ++k) {
                         const double bk = rb[k];
-                        const double viol = cdot(k, upv + j * LB) - bk;
+                        const double viol = cdotr(k, vb) - bk;
                         if (viol > 1e-9 * (1.0 + fabs(bk)) && !((amask[j] >> k) & 1)) amask[j] |= 1 << k, changed = true;
                     }
+                }
                 if (changed) continue;
                 // dual check: minus the gradient must be a non-negative combination of the active rows
                 grad(upv, tvp, nullptr);
@@ -911,8 +1186,11 @@ struct LaneSolver {
 
 #if defined(__CUDACC__) && !defined(BMPC_LANE_HOST_ONLY)
 // One warp = 32 robots of the class's work list at a time (dynamic: a global counter hands out 32-robot slices).
+#ifndef BMPC_LANE_MINB
+#define BMPC_LANE_MINB 3
+#endif
 template <int HZ, int NF, int LB>
-__global__ void __launch_bounds__(128) lane_tick_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
+__global__ void __launch_bounds__(128, BMPC_LANE_MINB) lane_tick_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
                                                         const int* __restrict__ work_list, const int* __restrict__ work_count,
                                                         int* __restrict__ slice_counter, double* __restrict__ wsbase) {
     using L = LaneL<HZ, NF, LB>;

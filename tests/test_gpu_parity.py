@@ -293,7 +293,7 @@ def test_mixed_contact_patterns(torch_cuda):
 
 
 def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
-    """The experimental lane-per-robot kernels (BMPC_LANE=1, csrc/bmpc_lane.cuh; one thread per robot, everything they do
+    """The experimental lane-per-robot kernels (BMPC_LANE=1|2, csrc/bmpc_lane.cuh; one thread per robot, everything they do
     not certify falls through to the warp-per-robot kernels) must return the same certified optimum as the default path:
     synthetic batch + arbitrary contact schedules (those are not the lane path's and exercise the fall-through)."""
     from biped_mpc_py_b200 import synth
@@ -307,7 +307,7 @@ def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
     ref_solver, _, _ = _solver(0, max_batch=n)
     ref = ref_solver.step_host(*args, want_states=True)
     ref_solver.close()
-    monkeypatch.setenv("BMPC_LANE", "1")
+    monkeypatch.setenv("BMPC_LANE", "2")  # 1: walking class only, 2: both classes
     monkeypatch.setenv("BMPC_LANE_MIN", "1")
     lane_solver, _, _ = _solver(0, max_batch=n)
     launches0 = lane_solver.launch_count
