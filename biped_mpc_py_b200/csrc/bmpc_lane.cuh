@@ -799,6 +799,7 @@ struct LaneSolver {
         int status = 1, it = 0;
         double mu = 0.0, rdmax = 0.0;
         bool rd_fresh = false;
+        double alpha_prev = 0.0;
 #pragma unroll 1
         while (true) {
             if (it >= p.max_iter) {
@@ -822,7 +823,16 @@ struct LaneSolver {
                 const int st = j / NF, li = j - st * NF;
                 double vb[LB], gacc[LB], acc[LB * (LB + 1) / 2];
 #pragma unroll
-                for (int c = 0; c < LB; ++c) vb[c] = uv[j * LB + c], gacc[c] = rdv[j * LB + c];
+                for (int c = 0; c < LB; ++c) {  // the previous iteration's step is applied here (alpha_prev = 0 in the first one)
+                    vb[c] = uv[j * LB + c];
+                    gacc[c] = rdv[j * LB + c];
+                    if (alpha_prev != 0.0) {  // (duv is uninitialised before the first step)
+                        vb[c] += alpha_prev * duv[j * LB + c];
+                        gacc[c] *= (1.0 - alpha_prev);
+                        uv[j * LB + c] = vb[c];
+                        rdv[j * LB + c] = gacc[c];
+                    }
+                }
 #pragma unroll
                 for (int a = 0; a < LB; ++a)
 #pragma unroll
@@ -830,14 +840,19 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
-                    const double s = r_s[r], l = r_l[r];
+                    double s = r_s[r], l = r_l[r];
+                    if (alpha_prev != 0.0) {
+                        s += alpha_prev * r_p[r];
+                        l += alpha_prev * r_c[r];
+                        r_s[r] = s;
+                        r_l[r] = l;
+                    }
                     double cb[LB];
                     crow(k, cb);
                     double cu = 0.0;
 #pragma unroll
                     for (int c = 0; c < LB; ++c) cu += cb[c] * vb[c];
                     const double d = l / s, rp = cu + s - rb[k];
-                    r_d[r] = d;
                     r_p[r] = rp;
                     const double w = d * rp - l;
                     part += s * l;
@@ -881,9 +896,10 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
+                    const double sr = r_s[r], lr = r_l[r];
                     const double dsa = -r_p[r] - cdotr(k, vb);
-                    const double dla = -r_l[r] - r_d[r] * dsa;
-                    ratio = fmaxf(ratio, fmaxf(sratio(dsa, r_s[r]), sratio(dla, r_l[r])));
+                    const double dla = -lr - (lr / sr) * dsa;
+                    ratio = fmaxf(ratio, fmaxf(sratio(dsa, sr), sratio(dla, lr)));
                     r_c[r] = dsa * dla;
                     part += dsa * dla;
                 }
@@ -893,9 +909,25 @@ struct LaneSolver {
             double sigma = mu_aff / mu;
             sigma = sigma * sigma * sigma;
             const double tgt = sigma * mu;
+            // corrector right-hand side C' wc, wc = (dsa dla - sigma mu) / s   (solved in duv, the affine step stays in xv)
 #pragma unroll 1
-            for (int r = 0; r < m; ++r) r_c[r] = (r_c[r] - tgt) / r_s[r];
-            gather(r_c, duv, 0.0, duv);  // corrector solved in duv, the affine step stays in xv
+            for (int j = 0; j < S; ++j) {
+                double gacc[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) gacc[c] = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < mb; ++k) {
+                    const int r = j * mb + k;
+                    const double wc = (r_c[r] - tgt) / r_s[r];
+                    r_c[r] = wc;
+                    double cb[LB];
+                    crow(k, cb);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) gacc[c] += cb[c] * wc;
+                }
+#pragma unroll
+                for (int c = 0; c < LB; ++c) duv[j * LB + c] = gacc[c];
+            }
             solve(duv);
 #pragma unroll 1
             for (int i = 0; i < N; ++i) duv[i] += xv[i];
@@ -908,9 +940,10 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
+                    const double sr = r_s[r], lr = r_l[r];
                     const double ds = -r_p[r] - cdotr(k, vb);
-                    const double dl = -r_l[r] - r_c[r] - r_d[r] * ds;
-                    ratio = fmaxf(ratio, fmaxf(sratio(ds, r_s[r]), sratio(dl, r_l[r])));
+                    const double dl = -lr - r_c[r] - (lr / sr) * ds;
+                    ratio = fmaxf(ratio, fmaxf(sratio(ds, sr), sratio(dl, lr)));
                     r_p[r] = ds;
                     r_c[r] = dl;
                 }
@@ -966,15 +999,9 @@ struct LaneSolver {
                     for (int i = 0; i < N; ++i) duv[i] += xv[i];
                 }
             }
-            const double alpha = (it > 14 ? 0.9 : p.step_frac) * a2;
-#pragma unroll 1
-            for (int r = 0; r < m; ++r) {
-                r_s[r] += alpha * r_p[r];
-                r_l[r] += alpha * r_c[r];
-            }
-#pragma unroll 1
-            for (int i = 0; i < N; ++i) uv[i] += alpha * duv[i], rdv[i] *= (1.0 - alpha);
-            rdmax *= (1.0 - alpha);
+            // the step (u, s, lam, rd) is applied by the next iteration's first pass
+            alpha_prev = (it > 14 ? 0.9 : p.step_frac) * a2;
+            rdmax *= (1.0 - alpha_prev);
         }
 
         // ---- 3. active-set polish + certificate (one attempt; anything else goes to the warp-per-robot kernels) ----
