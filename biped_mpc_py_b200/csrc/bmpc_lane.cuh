@@ -388,13 +388,14 @@ struct LaneSolver {
         for (int i = HZ - 1; i >= 0; --i) {
             SV Bv = ws + (L::o_Bm + 30 * i), Rt = ws + (L::o_Rt + 25 * i), ri = ws + (L::o_rinv + 9 * i);
             SV Y = ws + (L::o_K + 60 * i), Lc = ws + (L::o_Lc + 25 * i);
-            double B[6][5], lo[6][5], hi[6][5], Lr[5][5];
+            double B[6][5], lo[6][5], Lr[5][5];
 #pragma unroll
             for (int k = 0; k < 6; ++k)
 #pragma unroll
                 for (int c = 0; c < 5; ++c) B[k][c] = Bv[k * 5 + c];
+            // rows 6..11 of P B (they also feed G); rows 0..5 are produced one at a time below so that they are never all live
 #pragma unroll
-            for (int r = 0; r < 12; ++r) {
+            for (int r = 6; r < 12; ++r) {
                 double pr[6];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) pr[k] = P[pk(r, 6 + k)];
@@ -403,8 +404,7 @@ struct LaneSolver {
                     double acc = 0.0;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) acc += pr[k] * B[k][c];
-                    if (r < 6) hi[r][c] = acc;
-                    else lo[r - 6][c] = acc;
+                    lo[r - 6][c] = acc;
                 }
             }
             // G = Rt + B' PB[6:12], Cholesky in registers (reciprocal diagonal)
@@ -427,32 +427,49 @@ struct LaneSolver {
                 }
             }
             if (!ok) return false;
-            // F = PB' A in place (columns 6..11 live in lo), then Y = inv(L) F column by column
+            // F = PB' A: row j < 6 of P B is column j of F and also adds into columns 6..11 (kept in lo); Y = inv(L) F
             {
                 double r9[9];
 #pragma unroll
                 for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
+                for (int j = 0; j < 6; ++j) {
+                    double pr[6], h[5];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) pr[k] = P[pk(j, 6 + k)];
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
-                        lo[k][c] += hi[0][c] * r9[k] + hi[1][c] * r9[3 + k] + hi[2][c] * r9[6 + k];
-                        lo[3 + k][c] += dt * hi[3 + k][c];
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc += pr[k] * B[k][c];
+                        h[c] = acc;
+                        if (j < 3) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) lo[k][c] += acc * r9[3 * j + k];
+                        } else {
+                            lo[j][c] += dt * acc;
+                        }
                     }
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) {
+                        double v = h[a];
+#pragma unroll
+                        for (int k = 0; k < a; ++k) v -= Lr[a][k] * h[k];
+                        h[a] = v * Lr[a][a];
+                        Y[a * 12 + j] = h[a];
+                    }
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
+            for (int j = 0; j < 6; ++j)
 #pragma unroll
                 for (int a = 0; a < 5; ++a) {
-                    double vh = hi[j][a], vl = lo[j][a];
+                    double v = lo[j][a];
 #pragma unroll
-                    for (int k = 0; k < a; ++k) vh -= Lr[a][k] * hi[j][k], vl -= Lr[a][k] * lo[j][k];
-                    hi[j][a] = vh * Lr[a][a];
-                    lo[j][a] = vl * Lr[a][a];
+                    for (int k = 0; k < a; ++k) v -= Lr[a][k] * lo[j][k];
+                    lo[j][a] = v * Lr[a][a];
+                    Y[a * 12 + 6 + j] = lo[j][a];
                 }
-#pragma unroll
-                for (int a = 0; a < 5; ++a) Y[a * 12 + j] = hi[j][a], Y[a * 12 + 6 + j] = lo[j][a];
-            }
 #pragma unroll
             for (int a = 0; a < 5; ++a)
 #pragma unroll
