@@ -344,40 +344,35 @@ struct LaneSolver {
 
     // P <- A' P A on the packed triangle.  A = [I D; 0 I], D = dt [Rinv 0; 0 I]:  P21 += D' P11,  P22 += D' P12new + P21old D
     BMPC_HD void congruence_pk(SV P, SV ri) {
-        double r9[9], p11[21], o21[6][6], n21[6][6];
+        double r9[9], p11[21], n21[6][6];
 #pragma unroll
         for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
 #pragma unroll
         for (int e = 0; e < 21; ++e) p11[e] = P[e];
+        // row by row, so that a row of the old P21 dies as soon as its row of P22 is done
 #pragma unroll
-        for (int kp = 0; kp < 6; ++kp)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) o21[kp][c] = P[pk(6 + kp, c)];
-#pragma unroll
-        for (int kp = 0; kp < 3; ++kp)
+        for (int kp = 0; kp < 6; ++kp) {
+            double o[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
-                n21[kp][c] = o21[kp][c] + r9[kp] * p11[pk(0, c)] + r9[3 + kp] * p11[pk(1, c)] + r9[6 + kp] * p11[pk(2, c)];
-                n21[3 + kp][c] = o21[3 + kp][c] + dt * p11[pk(3 + kp, c)];
+                o[c] = P[pk(6 + kp, c)];
+                if (kp < 3) n21[kp][c] = o[c] + r9[kp] * p11[pk(0, c)] + r9[3 + kp] * p11[pk(1, c)] + r9[6 + kp] * p11[pk(2, c)];
+                else n21[kp][c] = o[c] + dt * p11[pk(kp, c)];
+                P[pk(6 + kp, c)] = n21[kp][c];
             }
-#pragma unroll
-        for (int kp = 0; kp < 6; ++kp)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) P[pk(6 + kp, c)] = n21[kp][c];
-#pragma unroll
-        for (int kp = 0; kp < 6; ++kp)
 #pragma unroll
             for (int k = 0; k <= kp; ++k) {
                 double t1, t2;
                 if (kp < 3) t1 = r9[kp] * n21[k][0] + r9[3 + kp] * n21[k][1] + r9[6 + kp] * n21[k][2];
                 else t1 = dt * n21[k][kp];
-                if (k < 3) t2 = o21[kp][0] * r9[k] + o21[kp][1] * r9[3 + k] + o21[kp][2] * r9[6 + k];
-                else t2 = dt * o21[kp][k];
+                if (k < 3) t2 = o[0] * r9[k] + o[1] * r9[3 + k] + o[2] * r9[6 + k];
+                else t2 = dt * o[k];
                 P[pk(6 + kp, 6 + k)] += t1 + t2;
             }
+        }
     }
 
-    BMPC_HD bool factor1() {
+    BMPC_HD __noinline__ bool factor1() {
         static_assert(LB == 5, "register-blocked sweep is written for 5 free components per block");
         SV P = ws + L::o_P;
 #pragma unroll 1
@@ -498,7 +493,7 @@ struct LaneSolver {
         return true;
     }
 
-    BMPC_HD void solve1(SV x) {
+    BMPC_HD __noinline__ void solve1(SV x) {
         double pv[12];
 #pragma unroll
         for (int a = 0; a < 12; ++a) pv[a] = 0.0;
