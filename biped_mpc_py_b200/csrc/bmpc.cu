@@ -42,6 +42,7 @@ typedef void (*LaneKernel)(const DevParams, const IoPtrs, const int*, const int*
 struct LaneVariant {
     LaneKernel fn = nullptr;
     int grid = 0;
+    size_t ws_doubles = 0;
     double* d_ws = nullptr;  // [warps][total][32] lane-interleaved work arrays
 };
 
@@ -115,14 +116,14 @@ int setup_variant(Variant& v, int num_sms, int mb) {
 }
 
 template <int HZ, int NF, int LB>
-int setup_lane(LaneVariant& v, int num_sms, int ctas_per_sm) {
+int setup_lane(LaneVariant& v, int num_sms, int ctas_per_sm, int max_batch) {
     v.fn = lane_tick_kernel<HZ, NF, LB>;
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, 128, 0));
     if (per_sm < 1) return fail("lane kernel does not fit on an SM");
     if (ctas_per_sm > 0) per_sm = std::min(per_sm, ctas_per_sm);
-    v.grid = per_sm * num_sms;
-    CUDA_TRY(cudaMalloc(&v.d_ws, sizeof(double) * (size_t)LaneL<HZ, NF, LB>::total * 32 * 4 * (size_t)v.grid));
+    v.grid = std::min(per_sm * num_sms, (max_batch + 127) / 128);
+    v.ws_doubles = (size_t)LaneL<HZ, NF, LB>::total * 32 * 4 * (size_t)v.grid;  // allocated on first use (throughput batches only)
     return 0;
 }
 
@@ -155,7 +156,8 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
             // throughput batches: one THREAD per robot first (32 robots share every instruction); robots it does not
             // certify (status 1) are collected and solved by the warp-per-robot kernel below
             int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
-            h->lane[b].fn<<<h->lane[b].grid, 128, 0, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b, h->lane[b].d_ws);
+            if (!h->lane[b].d_ws) CUDA_TRY(cudaMalloc(&h->lane[b].d_ws, sizeof(double) * h->lane[b].ws_doubles));
+            h->lane[b].fn<<<std::min(h->lane[b].grid, (n + 127) / 128), 128, 0, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b, h->lane[b].d_ws);
             collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b);
             list = rlist, cnt = h->d_counts + 6 + b;
             h->launches += 2;
@@ -256,16 +258,18 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         else
 #endif
             if (!rc) rc = setup_variant<10, 20, 5, 128, 1>(h->bucket[1], sms, mb);  // standing: one 128-thread CTA per robot
-        // Lane-per-robot front end (bmpc_lane.cuh): EXPERIMENT, off unless BMPC_LANE=1.  Correct (every robot certified, GPU
-        // parity tests green with it on) but slower than the warp-per-robot kernels in its first form: its per-robot work
-        // arrays (30 KB) live in global memory and the kernel is L1/L2-traffic bound (profiles/r1_summary.md, "lane").
+        // Lane-per-robot front end (bmpc_lane.cuh) for throughput batches (n >= lane_min): one THREAD per robot, 32 robots per
+        // instruction; whatever it does not certify falls through to the warp-per-robot kernel of the class.  Default: the
+        // walking class (69 ms vs 92 ms per 222,800 robots); the standing-class version is not register-blocked yet and is
+        // slower than its warp-per-robot kernel (BMPC_LANE=2 enables it, BMPC_LANE=0 disables the front end altogether).
         const char* ela = getenv("BMPC_LANE");
-        if (!rc && ela && atoi(ela) != 0) {
+        const int lane_mode = ela ? atoi(ela) : 1;
+        if (!rc && lane_mode != 0) {
             const char* elm = getenv("BMPC_LANE_MIN");
             h->lane_min = elm ? atoi(elm) : 2048;
             const char* elc = getenv("BMPC_LANE_CTAS");  // CTAs (4 warps = 128 robots each) per SM
-            rc = setup_lane<10, 1, 5>(h->lane[0], sms, elc ? atoi(elc) : 0);               // BMPC_LANE=1: walking class only
-            if (!rc && atoi(ela) >= 2) rc = setup_lane<10, 2, 5>(h->lane[1], sms, elc ? atoi(elc) : 0);  // 2: both classes
+            rc = setup_lane<10, 1, 5>(h->lane[0], sms, elc ? atoi(elc) : 0, max_batch);
+            if (!rc && lane_mode >= 2) rc = setup_lane<10, 2, 5>(h->lane[1], sms, elc ? atoi(elc) : 0, max_batch);
         }
         const char* ell = getenv("BMPC_LOWLAT");  // 0 disables the low-latency walking variant for batches <= 8
         if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, sms, mb);

@@ -293,8 +293,9 @@ def test_mixed_contact_patterns(torch_cuda):
 
 
 def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
-    """The experimental lane-per-robot kernels (BMPC_LANE=1|2, csrc/bmpc_lane.cuh; one thread per robot, everything they do
-    not certify falls through to the warp-per-robot kernels) must return the same certified optimum as the default path:
+    """The lane-per-robot kernels (csrc/bmpc_lane.cuh; one thread per robot, front end of the walking class for batches >= 2048
+    by default, BMPC_LANE=2 for both classes; everything they do not certify falls through to the warp-per-robot kernels) must
+    return the same certified optimum as the warp-per-robot kernels alone (BMPC_LANE=0):
     synthetic batch + arbitrary contact schedules (those are not the lane path's and exercise the fall-through)."""
     from biped_mpc_py_b200 import synth
     n = 2048
@@ -304,8 +305,11 @@ def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
     b["contact"][:64] = (rng.uniform(size=(64, 10, 2)) < 0.6).astype(np.uint8)
     b["x_fb"][64, 1] = np.nan  # bad input must still be flagged through the fall-through
     args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+    monkeypatch.setenv("BMPC_LANE", "0")  # warp-per-robot kernels only
     ref_solver, _, _ = _solver(0, max_batch=n)
+    launches0 = ref_solver.launch_count
     ref = ref_solver.step_host(*args, want_states=True)
+    assert ref_solver.launch_count - launches0 == 3
     ref_solver.close()
     monkeypatch.setenv("BMPC_LANE", "2")  # 1: walking class only, 2: both classes
     monkeypatch.setenv("BMPC_LANE_MIN", "1")
