@@ -81,9 +81,36 @@ def flops_per_solve(S, iters, LB=5, mb=11, h=10, stages=None, polish_rounds=1.15
     return f_setup + iters * f_iter + (polish_rounds * f_polish if S > 0 else 0.0) + 600.0
 
 
-def batch_flops(contact, iters):
+def flops_per_solve_lane(S, iters, LB=5, mb=11, h=10, polish_rounds=1.15):
+    """Restated for the stage-wise (Riccati) factorisation of the lane-per-robot kernel (SURVEY.md 8d asks for that when
+    the factorisation differs): per stage with one stance foot the sweep is 1,211 FMA (P B 360, G + Cholesky
+    125, F column operation 60, Y = inv(L) F 120, congruence 156, rank-5 update 390), a solve 224 FMA (backward + forward);
+    one iteration = one sweep + two solves (no Gondzio corrector in this kernel) + the row passes + the stage weights."""
+    m = mb * S
+    per_foot = S / float(h)
+    f_sweep, f_solve, f_grad = 2.0 * 1211.0 * h * per_foot, 2.0 * 224.0 * h * per_foot, 2.0 * 120.0 * h * per_foot
+    f_setup = 250.0 * h + 40.0 * S * h + f_grad
+    f_iter = f_sweep + 2.0 * f_solve + m * (8.0 * LB + 20.0) + S * mb * LB * (LB + 1.0)
+    f_polish = f_sweep + f_solve + 3.0 * f_grad + 4.0 * LB ** 3 * S
+    return f_setup + iters * f_iter + (polish_rounds * f_polish if S > 0 else 0.0) + 600.0
+
+
+def lane_front_end_active(n, h=10):
+    """Mirror of bmpc.cu: the lane-per-robot kernel solves the walking class of batches >= BMPC_LANE_MIN (default 2048)."""
+    return h == 10 and os.environ.get("BMPC_LANE", "1") != "0" and n >= int(os.environ.get("BMPC_LANE_MIN", "2048"))
+
+
+def batch_flops(contact, iters, lane=False):
     S = contact.reshape(contact.shape[0], -1).sum(axis=1).astype(int)
+    per_stage = contact.reshape(contact.shape[0], -1, 2).sum(axis=2)
+    one_foot = (per_stage == 1).all(axis=1)
     total = {0: 0.0, 1: 0.0}
+    if lane:  # robots with exactly one stance foot per stage are the lane kernel's
+        sel = one_foot
+        base = flops_per_solve_lane(contact.shape[1], 0.0)
+        per_it = flops_per_solve_lane(contact.shape[1], 1.0) - base
+        total[0] += sel.sum() * base + float(iters[sel].sum()) * per_it
+        contact, iters, S = contact[~sel], iters[~sel], S[~sel]
     for s_val in np.unique(S):
         sel = S == s_val
         cls = 0 if s_val <= 10 else 1
@@ -312,10 +339,14 @@ def run_b200(args, rank, local_rank, world):
         kt.append(solver.last_timing_ms())
     solver.enable_timing(False)
     kt = np.array(kt).mean(axis=0)  # classify, walking-class, standing-class
-    fl = batch_flops(batch["contact"], iters)
+    lane = lane_front_end_active(n)
+    fl = batch_flops(batch["contact"], iters, lane=lane)
     peaks = measure(local_rank)
     kernels = []
-    for cls, name in ((0, "mpc_tick2_kernel<10,10,5,32,8> (<=10 stance foot-stages: walking class, one warp per robot, 8 robots per CTA)"),
+    walk_name = ("lane_tick_kernel<10,1,5> (walking class: one THREAD per robot, stage-wise Riccati sweep; + collect + "
+                 "mpc_tick2_kernel<10,10,5,32,8> for what it does not certify)") if lane else \
+        "mpc_tick2_kernel<10,10,5,32,8> (<=10 stance foot-stages: walking class, one warp per robot, 8 robots per CTA)"
+    for cls, name in ((0, walk_name),
                       (1, "mpc_tick2_kernel<10,20,5,128,1> (11..20 stance foot-stages: standing class, one CTA per robot)")):
         ach = fl[cls] / (kt[1 + cls] * 1e-3) / 1e12 if kt[1 + cls] > 0 else 0.0
         kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
@@ -342,6 +373,19 @@ def run_b200(args, rank, local_rank, world):
                 "kernels": kernels, "classify_ms": float(kt[0]),
                 "share_of_step": {"walking": float(kt[1] / kt.sum()), "standing": float(kt[2] / kt.sum())},
                 "secondary": secondary}
+    if traffic is not None and kernels[dom]["ms_per_launch"] > 0:
+        # the lane-per-robot kernel streams its per-robot work arrays through DRAM: report that against the measured copy bandwidth
+        hbm_peak = 6543.1
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        gbs = traffic / 1e9 / (kernels[dom]["ms_per_launch"] * 1e-3)
+        roofline["hbm_view"] = {"what": "measured DRAM bytes of the dominant kernel (ncu, profiles/traffic.json) / its live duration: work-array "
+                                        "streaming, not algorithmic bytes (~1.5 KB per robot)",
+                                "dram_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak,
+                                "dram_bytes_per_robot": traffic / max(1, int((batch["contact"].reshape(n, -1, 2).sum(axis=2) == 1).all(axis=1).sum()))
+                                if lane else None}
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------
     tick = solver.pinned_tick(n, lowlevel=True, want_states=False)
