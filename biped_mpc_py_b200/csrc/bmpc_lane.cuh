@@ -58,6 +58,7 @@ struct LaneL {
 template <int HZ, int NF, int LB>
 struct LaneSolver {
     using L = LaneL<HZ, NF, LB>;
+    static_assert(LB == 5, "the input-map / weight layouts below are the block layouts of the register-blocked LB = 5 sweep");
     static constexpr int NU = L::NU, S = L::S, N = L::N, E = L::E;
     const DevParams& p;
     SV ws;
@@ -157,7 +158,7 @@ struct LaneSolver {
 
     // ---- backward Riccati sweep: factors  blockdiag(Rt) + B' (state cost) B  in stage-wise form --------------------
     BMPC_HD bool factor() {
-        if constexpr (NF == 1 && LB == 5) return factor1();
+        if constexpr (LB == 5) return factor1();
         SV P = ws + L::o_P, PB = ws + L::o_PB, F = ws + L::o_F, G = ws + L::o_G;
 #pragma unroll 1
         for (int e = 0; e < 144; ++e) P[e] = 0.0;
@@ -263,7 +264,7 @@ struct LaneSolver {
 
     // x <- inv(M) x  with the factor of the last factor() call
     BMPC_HD void solve(SV x) {
-        if constexpr (NF == 1 && LB == 5) {
+        if constexpr (LB == 5) {
             solve1(x);
             return;
         }
@@ -336,7 +337,8 @@ struct LaneSolver {
     }
 
 
-    // ---- NF == 1 (walking class): register-blocked stage sweep; cost-to-go kept as a packed lower triangle (78) ----
+    // ---- LB == 5: register-blocked sweep over VIRTUAL stages of one block (5 inputs) each; cost-to-go kept as a packed
+    //      lower triangle (78).  A stage with two stance feet is two virtual stages: Z = A X + B_0 u_0, then X' = Z + B_1 u_1 ----
     // Per stage the only global traffic is P (read for P B, the congruence and the rank-NU update), B, Rt, and the factor
     // pieces the solves need:  Y = inv(L) F  (NU x 12) and L  (G = L L').  K = inv(L') Y is never formed:
     // K z = inv(L') (Y z),  K' g = Y' (inv(L) g),  F' inv(G) F = Y' Y.
@@ -380,9 +382,14 @@ struct LaneSolver {
 #pragma unroll
         for (int a = 0; a < 12; ++a) P[pk(a, a)] = p.Q[a];
 #pragma unroll 1
-        for (int i = HZ - 1; i >= 0; --i) {
-            SV Bv = ws + (L::o_Bm + 30 * i), Rt = ws + (L::o_Rt + 25 * i), ri = ws + (L::o_rinv + 9 * i);
-            SV Y = ws + (L::o_K + 60 * i), Lc = ws + (L::o_Lc + 25 * i);
+        for (int v = S - 1; v >= 0; --v) {
+            // virtual stage v = block (stage st, foot slot li): the first block of a stage carries the dynamics A_st and the
+            // state cost of the state before it, the others act on the intermediate state (A = I, no cost)
+            const int st = v / NF;
+            const bool dyn = (v - st * NF) == 0;
+            const double dte = dyn ? dt : 0.0;
+            SV Bv = ws + (L::o_Bm + 30 * v), Rt = ws + (L::o_Rt + 25 * v), ri = ws + (L::o_rinv + 9 * st);
+            SV Y = ws + (L::o_K + 60 * v), Lc = ws + (L::o_Lc + 25 * v);
             double B[6][5], lo[6][5], Lr[5][5];
 #pragma unroll
             for (int k = 0; k < 6; ++k)
@@ -426,7 +433,7 @@ struct LaneSolver {
             {
                 double r9[9];
 #pragma unroll
-                for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
+                for (int a = 0; a < 9; ++a) r9[a] = dte * ri[a];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     double pr[6], h[5];
@@ -442,7 +449,7 @@ struct LaneSolver {
 #pragma unroll
                             for (int k = 0; k < 3; ++k) lo[k][c] += acc * r9[3 * j + k];
                         } else {
-                            lo[j][c] += dt * acc;
+                            lo[j][c] += dte * acc;
                         }
                     }
 #pragma unroll
@@ -469,9 +476,9 @@ struct LaneSolver {
             for (int a = 0; a < 5; ++a)
 #pragma unroll
                 for (int k = 0; k <= a; ++k) Lc[a * 5 + k] = Lr[a][k];
-            if (i == 0) break;
-            // P <- Q + A' P A - Y' Y
-            congruence_pk(P, ri);
+            if (v == 0) break;
+            // P <- [Q] + A' P A - Y' Y
+            if (dyn) congruence_pk(P, ri);
             {
                 double Yr[5][12];
 #pragma unroll
@@ -485,7 +492,7 @@ struct LaneSolver {
                         double acc = P[pk(r, c)];
 #pragma unroll
                         for (int a = 0; a < 5; ++a) acc -= Yr[a][r] * Yr[a][c];
-                        if (r == c) acc += p.Q[r];
+                        if (r == c && dyn) acc += p.Q[r];
                         P[pk(r, c)] = acc;
                     }
             }
@@ -498,9 +505,11 @@ struct LaneSolver {
 #pragma unroll
         for (int a = 0; a < 12; ++a) pv[a] = 0.0;
 #pragma unroll 1
-        for (int i = HZ - 1; i >= 0; --i) {
-            SV Bv = ws + (L::o_Bm + 30 * i), ri = ws + (L::o_rinv + 9 * i), Y = ws + (L::o_K + 60 * i), Lc = ws + (L::o_Lc + 25 * i),
-               xi = x + 5 * i;
+        for (int v = S - 1; v >= 0; --v) {
+            const int st = v / NF;
+            const double dte = ((v - st * NF) == 0) ? dt : 0.0;
+            SV Bv = ws + (L::o_Bm + 30 * v), ri = ws + (L::o_rinv + 9 * st), Y = ws + (L::o_K + 60 * v), Lc = ws + (L::o_Lc + 25 * v),
+               xi = x + 5 * v;
             double w[5];
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
@@ -517,8 +526,8 @@ struct LaneSolver {
             for (int a = 0; a < 12; ++a) np[a] = pv[a];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                np[6 + k] += dt * (ri[k] * pv[0] + ri[3 + k] * pv[1] + ri[6 + k] * pv[2]);
-                np[9 + k] += dt * pv[3 + k];
+                np[6 + k] += dte * (ri[k] * pv[0] + ri[3 + k] * pv[1] + ri[6 + k] * pv[2]);
+                np[9 + k] += dte * pv[3 + k];
             }
 #pragma unroll
             for (int a = 0; a < 5; ++a)
@@ -531,9 +540,11 @@ struct LaneSolver {
 #pragma unroll
         for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
-        for (int i = 0; i < HZ; ++i) {
-            SV Bv = ws + (L::o_Bm + 30 * i), ri = ws + (L::o_rinv + 9 * i), Y = ws + (L::o_K + 60 * i), Lc = ws + (L::o_Lc + 25 * i),
-               xi = x + 5 * i;
+        for (int v = 0; v < S; ++v) {
+            const int st = v / NF;
+            const double dte = ((v - st * NF) == 0) ? dt : 0.0;
+            SV Bv = ws + (L::o_Bm + 30 * v), ri = ws + (L::o_rinv + 9 * st), Y = ws + (L::o_K + 60 * v), Lc = ws + (L::o_Lc + 25 * v),
+               xi = x + 5 * v;
             double t[5], xs[5];
 #pragma unroll
             for (int a = 0; a < 5; ++a) {
@@ -559,8 +570,8 @@ struct LaneSolver {
             }
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                z[a] += dt * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
-                z[3 + a] += dt * z[9 + a];
+                z[a] += dte * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
+                z[3 + a] += dte * z[9 + a];
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) z[6 + k] += acc[k];
@@ -805,7 +816,11 @@ struct LaneSolver {
 #pragma unroll 1
         for (int r = 0; r < m; ++r) r_l[r] = mu0 / r_s[r];
 #pragma unroll 1
-        for (int e = 0; e < HZ * 6 * NU; ++e) ws[L::o_Bm + e] = ws[L::o_B0 + e];
+        for (int j = 0; j < S; ++j) {  // input maps in use, block layout [block][6][LB] (the problem's maps B0 are [stage][6][NU])
+            const int st = j / NF, li = j - st * NF;
+            for (int k = 0; k < 6; ++k)
+                for (int c = 0; c < LB; ++c) ws[L::o_Bm + (j * 6 + k) * LB + c] = ws[L::o_B0 + 6 * NU * st + k * NU + li * LB + c];
+        }
 
         const double mu_target = p.mu_tol * gs;
         int status = 1, it = 0;
@@ -877,16 +892,11 @@ struct LaneSolver {
                 }
 #pragma unroll
                 for (int c = 0; c < LB; ++c) xv[j * LB + c] = -gacc[c];
-                SV Rt = ws + (L::o_Rt + NU * NU * st);
-                if (NF > 1 && li == 0)
-                    for (int e = 0; e < NU * NU; ++e) Rt[e] = 0.0;
+                SV Rt = ws + (L::o_Rt + LB * LB * j);  // block layout: the sweep reads one LB x LB block per virtual stage
 #pragma unroll
                 for (int a = 0; a < LB; ++a)
 #pragma unroll
-                    for (int b2 = 0; b2 <= a; ++b2) {
-                        Rt[(li * LB + a) * NU + li * LB + b2] = acc[a * (a + 1) / 2 + b2];
-                        Rt[(li * LB + b2) * NU + li * LB + a] = acc[a * (a + 1) / 2 + b2];
-                    }
+                    for (int b2 = 0; b2 <= a; ++b2) Rt[a * LB + b2] = acc[a * (a + 1) / 2 + b2];
             }
             mu = part / (double)m;
             if (mu <= mu_target && rdmax <= p.rd_tol * mu_target) {
@@ -1077,12 +1087,10 @@ struct LaneSolver {
                 // reduced LQR: inputs w_b, maps B_b N_b, weights N_b' R N_b (+ I on the padding)
 #pragma unroll 1
                 for (int s = 0; s < HZ; ++s) {
-                    SV Rt = ws + (L::o_Rt + NU * NU * s), B0 = ws + (L::o_B0 + 6 * NU * s), Bm = ws + (L::o_Bm + 6 * NU * s);
-                    if (NF > 1)
-                        for (int e = 0; e < NU * NU; ++e) Rt[e] = 0.0;
+                    SV B0 = ws + (L::o_B0 + 6 * NU * s);
                     for (int li = 0; li < NF; ++li) {
                         const int j = s * NF + li, dim = bdim[j];
-                        SV Nj = Nn + j * E;
+                        SV Nj = Nn + j * E, Rt = ws + (L::o_Rt + LB * LB * j), Bm = ws + (L::o_Bm + 6 * LB * j);  // block layouts
 #pragma unroll 1
                         for (int a = 0; a < LB; ++a) {
                             double acc = 0.0;
@@ -1095,15 +1103,14 @@ struct LaneSolver {
 #pragma unroll
                                 for (int c = 0; c < LB; ++c) w += Nj[c * LB + a] * Rd[fo[j]][c] * Nj[c * LB + b];
                                 if (a == b && a >= dim) w = 1.0;
-                                Rt[(li * LB + a) * NU + li * LB + b] = w;
-                                Rt[(li * LB + b) * NU + li * LB + a] = w;
+                                Rt[a * LB + b] = w;
                             }
 #pragma unroll
                             for (int k = 0; k < 6; ++k) {
                                 double w = 0.0;
 #pragma unroll
                                 for (int c = 0; c < LB; ++c) w += B0[k * NU + li * LB + c] * Nj[c * LB + a];
-                                Bm[k * NU + li * LB + a] = w;
+                                Bm[k * LB + a] = w;
                             }
                         }
                     }
