@@ -97,20 +97,21 @@ def flops_per_solve_lane(S, iters, LB=5, mb=11, h=10, polish_rounds=1.15):
 
 def lane_front_end_active(n, h=10):
     """Mirror of bmpc.cu: the lane-per-robot kernel solves the walking class of batches >= BMPC_LANE_MIN (default 2048)."""
-    return h == 10 and os.environ.get("BMPC_LANE", "1") != "0" and n >= int(os.environ.get("BMPC_LANE_MIN", "2048"))
+    return h == 10 and os.environ.get("BMPC_LANE", "2") != "0" and n >= int(os.environ.get("BMPC_LANE_MIN", "2048"))
 
 
-def batch_flops(contact, iters, lane=False):
+def batch_flops(contact, iters, lane=False, lane_both=False):
     S = contact.reshape(contact.shape[0], -1).sum(axis=1).astype(int)
     per_stage = contact.reshape(contact.shape[0], -1, 2).sum(axis=2)
-    one_foot = (per_stage == 1).all(axis=1)
     total = {0: 0.0, 1: 0.0}
-    if lane:  # robots with exactly one stance foot per stage are the lane kernel's
-        sel = one_foot
-        base = flops_per_solve_lane(contact.shape[1], 0.0)
-        per_it = flops_per_solve_lane(contact.shape[1], 1.0) - base
-        total[0] += sel.sum() * base + float(iters[sel].sum()) * per_it
-        contact, iters, S = contact[~sel], iters[~sel], S[~sel]
+    h = contact.shape[1]
+    for cls, feet in (((0, 1),) + (((1, 2),) if lane_both else ())) if lane else ():
+        # robots with exactly `feet` stance feet in every stage are the lane kernel's (S = feet * h blocks = virtual stages)
+        sel = (per_stage == feet).all(axis=1)
+        base = flops_per_solve_lane(feet * h, 0.0, h=h)
+        per_it = flops_per_solve_lane(feet * h, 1.0, h=h) - base
+        total[cls] += sel.sum() * base + float(iters[sel].sum()) * per_it
+        contact, iters, S, per_stage = contact[~sel], iters[~sel], S[~sel], per_stage[~sel]
     for s_val in np.unique(S):
         sel = S == s_val
         cls = 0 if s_val <= 10 else 1
@@ -340,17 +341,24 @@ def run_b200(args, rank, local_rank, world):
     solver.enable_timing(False)
     kt = np.array(kt).mean(axis=0)  # classify, walking-class, standing-class
     lane = lane_front_end_active(n)
-    fl = batch_flops(batch["contact"], iters, lane=lane)
+    lane_both = lane and os.environ.get("BMPC_LANE", "2") not in ("0", "1")
+    fl = batch_flops(batch["contact"], iters, lane=lane, lane_both=lane_both)
+    fl_dense = batch_flops(batch["contact"], iters)
     peaks = measure(local_rank)
     kernels = []
     walk_name = ("lane_tick_kernel<10,1,5> (walking class: one THREAD per robot, stage-wise Riccati sweep; + collect + "
                  "mpc_tick2_kernel<10,10,5,32,8> for what it does not certify)") if lane else \
         "mpc_tick2_kernel<10,10,5,32,8> (<=10 stance foot-stages: walking class, one warp per robot, 8 robots per CTA)"
-    for cls, name in ((0, walk_name),
-                      (1, "mpc_tick2_kernel<10,20,5,128,1> (11..20 stance foot-stages: standing class, one CTA per robot)")):
+    stand_name = ("lane_tick_kernel<10,2,5> (standing class: one THREAD per robot, two virtual stages of one 5-input block per stage; "
+                  "+ collect + mpc_tick2_kernel<10,20,5,128,1> for what it does not certify)") if lane_both else \
+        "mpc_tick2_kernel<10,20,5,128,1> (11..20 stance foot-stages: standing class, one CTA per robot)"
+    for cls, name in ((0, walk_name), (1, stand_name)):
         ach = fl[cls] / (kt[1 + cls] * 1e-3) / 1e12 if kt[1 + cls] > 0 else 0.0
         kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
-                        "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"]})
+                        "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"],
+                        # the same launch priced with the DENSE condensed-form count of the warp-per-robot kernels: the
+                        # stage-wise form needs 1.7x (walking) / 5x (standing) fewer FLOPs for the same solves
+                        "frac_at_dense_flop_count": (fl_dense[cls] / (kt[1 + cls] * 1e-3) / 1e12 / peaks["fp64_fma_tflops"]) if kt[1 + cls] > 0 else 0.0})
     dom = int(np.argmax(kt[1:]))
     traffic, secondary = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from one ncu capture of this batch size
