@@ -95,9 +95,15 @@ def flops_per_solve_lane(S, iters, LB=5, mb=11, h=10, polish_rounds=1.15):
     return f_setup + iters * f_iter + (polish_rounds * f_polish if S > 0 else 0.0) + 600.0
 
 
-def lane_front_end_active(n, h=10):
-    """Mirror of bmpc.cu: the lane-per-robot kernel solves the walking class of batches >= BMPC_LANE_MIN (default 2048)."""
-    return h == 10 and os.environ.get("BMPC_LANE", "2") != "0" and n >= int(os.environ.get("BMPC_LANE_MIN", "2048"))
+def lane_front_end_active(n, class_count, cls, h=10):
+    """Mirror of the size gates in bmpc.cu / lane_tick_kernel: the lane-per-robot kernel takes a class only when the batch has
+    >= 20,480 robots and the class >= 49,152 (walking) / 20,480 (standing) robots; BMPC_LANE_MIN overrides all three."""
+    mode = os.environ.get("BMPC_LANE", "2")
+    if h != 10 or mode == "0" or (cls == 1 and mode == "1"):
+        return False
+    ov = os.environ.get("BMPC_LANE_MIN")
+    n_min, c_min = (int(ov), int(ov)) if ov else (20480, (49152, 20480)[cls])
+    return n >= n_min and class_count >= c_min
 
 
 def batch_flops(contact, iters, lane=False, lane_both=False):
@@ -340,8 +346,9 @@ def run_b200(args, rank, local_rank, world):
         kt.append(solver.last_timing_ms())
     solver.enable_timing(False)
     kt = np.array(kt).mean(axis=0)  # classify, walking-class, standing-class
-    lane = lane_front_end_active(n)
-    lane_both = lane and os.environ.get("BMPC_LANE", "2") not in ("0", "1")
+    cls_count = np.bincount((batch["contact"].reshape(n, -1).sum(axis=1) > 10).astype(int), minlength=2)
+    lane = lane_front_end_active(n, int(cls_count[0]), 0)
+    lane_both = lane and lane_front_end_active(n, int(cls_count[1]), 1)
     fl = batch_flops(batch["contact"], iters, lane=lane, lane_both=lane_both)
     fl_dense = batch_flops(batch["contact"], iters)
     peaks = measure(local_rank)

@@ -36,13 +36,14 @@ int fail(const std::string& msg) {
 
 typedef void (*TickKernel)(const DevParams, const IoPtrs, const int*, const int*, double*);
 
-typedef void (*LaneKernel)(const DevParams, const IoPtrs, const int*, const int*, int*, double*);
+typedef void (*LaneKernel)(const DevParams, const IoPtrs, const int*, const int*, int*, double*, int);
 
 // lane-per-robot front end of one class (bmpc_lane.cuh): what it certifies is done, the rest goes to the class's Variant
 struct LaneVariant {
     LaneKernel fn = nullptr;
     int grid = 0;
     size_t ws_doubles = 0;
+    int min_count = 0;       // classes smaller than this stay on the warp-per-robot kernel (decided on the device)
     double* d_ws = nullptr;  // [warps][total][32] lane-interleaved work arrays
 };
 
@@ -157,8 +158,9 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
             // certify (status 1) are collected and solved by the warp-per-robot kernel below
             int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
             if (!h->lane[b].d_ws) CUDA_TRY(cudaMalloc(&h->lane[b].d_ws, sizeof(double) * h->lane[b].ws_doubles));
-            h->lane[b].fn<<<std::min(h->lane[b].grid, (n + 127) / 128), 128, 0, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b, h->lane[b].d_ws);
-            collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b);
+            h->lane[b].fn<<<std::min(h->lane[b].grid, (n + 127) / 128), 128, 0, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b, h->lane[b].d_ws,
+                                                                                       h->lane[b].min_count);
+            collect_or_all_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b, h->lane[b].min_count);
             list = rlist, cnt = h->d_counts + 6 + b;
             h->launches += 2;
         }
@@ -265,8 +267,15 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         const char* ela = getenv("BMPC_LANE");
         const int lane_mode = ela ? atoi(ela) : 2;
         if (!rc && lane_mode != 0) {
+            // Size gates.  One 32-robot slice takes ~20 ms however small the batch, so the front end pays only when a class fills
+            // the machine: measured crossover ~46 k walking / ~16 k standing robots (65,536-robot batch: 18.9 vs 23.0 ms walking,
+            // 23.5 vs 14.3 ms standing; 262,144: 69 vs 92 and 31 vs 57 ms).  The class sizes are only known on the device, so the
+            // lane kernel itself returns at once for a small class and collect_or_all_kernel passes the whole list on.
+            // BMPC_LANE_MIN overrides all three gates (tests use 1).
             const char* elm = getenv("BMPC_LANE_MIN");
-            h->lane_min = elm ? atoi(elm) : 2048;
+            h->lane_min = elm ? atoi(elm) : 20480;
+            h->lane[0].min_count = elm ? atoi(elm) : 49152;
+            h->lane[1].min_count = elm ? atoi(elm) : 20480;
             const char* elc = getenv("BMPC_LANE_CTAS");  // CTAs (4 warps = 128 robots each) per SM
             rc = setup_lane<10, 1, 5>(h->lane[0], sms, elc ? atoi(elc) : 0, max_batch);
             if (!rc && lane_mode >= 2) rc = setup_lane<10, 2, 5>(h->lane[1], sms, elc ? atoi(elc) : 0, max_batch);

@@ -1235,11 +1235,14 @@ struct LaneSolver {
 template <int HZ, int NF, int LB>
 __global__ void __launch_bounds__(128, BMPC_LANE_MINB) lane_tick_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
                                                         const int* __restrict__ work_list, const int* __restrict__ work_count,
-                                                        int* __restrict__ slice_counter, double* __restrict__ wsbase) {
+                                                        int* __restrict__ slice_counter, double* __restrict__ wsbase, int min_count) {
     using L = LaneL<HZ, NF, LB>;
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int count = *work_count;
+    // a class too small to fill the machine with 32-robot slices is faster on the warp-per-robot kernel (one slice takes
+    // ~20 ms whatever the batch): leave it alone, collect_or_all_kernel then hands the whole list over
+    if (count < min_count) return;
     SV ws{wsbase + (size_t)warp * L::total * 32 + lane};
     while (true) {
         int base = 0;

@@ -33,6 +33,23 @@ __global__ void collect_uncertified_kernel(const int* __restrict__ list, const i
     if (st == 1 || st == 2) out_list[atomicAdd(out_count, 1)] = inst;
 }
 
+// after a lane-per-robot front end: the robots it did not certify, or the whole list when the class was below the front end's
+// minimum size (it did not run then and status[] is stale)
+__global__ void collect_or_all_kernel(const int* __restrict__ list, const int* __restrict__ count, const int32_t* __restrict__ status,
+                                      int* __restrict__ out_list, int* __restrict__ out_count, int min_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = *count;
+    if (i >= c) return;
+    const int inst = list[i];
+    if (c < min_count) {
+        out_list[i] = inst;
+        if (i == 0) *out_count = c;
+        return;
+    }
+    const int st = status[inst];
+    if (st == 1 || st == 2) out_list[atomicAdd(out_count, 1)] = inst;
+}
+
 // lowLevelControl only (MPC.py:444-470): one thread per (instance, leg)
 __global__ void lowlevel_kernel(const __grid_constant__ DevParams p, int n, const double* __restrict__ x_fb,
                                 const double* __restrict__ t_swing, const double* __restrict__ pf_w,
