@@ -293,9 +293,9 @@ def test_mixed_contact_patterns(torch_cuda):
 
 
 def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
-    """The lane-per-robot kernels (csrc/bmpc_lane.cuh; one thread per robot, front end of the walking class for batches >= 2048
-    by default, BMPC_LANE=2 for both classes; everything they do not certify falls through to the warp-per-robot kernels) must
-    return the same certified optimum as the warp-per-robot kernels alone (BMPC_LANE=0):
+    """The lane-per-robot kernels (csrc/bmpc_lane.cuh; one thread per robot, front end of both classes when a class has enough
+    robots to fill the machine - BMPC_LANE_MIN=1 removes that gate here; everything they do not certify falls through to the
+    warp-per-robot kernels) must return the same certified optimum as the warp-per-robot kernels alone (BMPC_LANE=0):
     synthetic batch + arbitrary contact schedules (those are not the lane path's and exercise the fall-through)."""
     from biped_mpc_py_b200 import synth
     n = 2048
