@@ -29,6 +29,21 @@ struct SV {  // strided view of one lane's slice of the workspace
     double* p;
     BMPC_HD __forceinline__ double& operator[](int i) const { return p[(size_t)i * BMPC_LS]; }
     BMPC_HD __forceinline__ SV operator+(int o) const { return SV{p + (size_t)o * BMPC_LS}; }
+    // streaming read: data that will not be touched again before it is evicted anyway (the stored factor in the solves)
+    BMPC_HD __forceinline__ void sts(int i, double v) const {
+#ifdef __CUDA_ARCH__
+        __stcs(p + (size_t)i * BMPC_LS, v);
+#else
+        p[(size_t)i * BMPC_LS] = v;
+#endif
+    }
+    BMPC_HD __forceinline__ double lds(int i) const {
+#ifdef __CUDA_ARCH__
+        return __ldcs(p + (size_t)i * BMPC_LS);
+#else
+        return p[(size_t)i * BMPC_LS];
+#endif
+    }
 };
 
 template <int HZ, int NF, int LB>
@@ -156,186 +171,9 @@ struct LaneSolver {
         }
     }
 
-    // ---- backward Riccati sweep: factors  blockdiag(Rt) + B' (state cost) B  in stage-wise form --------------------
-    BMPC_HD bool factor() {
-        if constexpr (LB == 5) return factor1();
-        SV P = ws + L::o_P, PB = ws + L::o_PB, F = ws + L::o_F, G = ws + L::o_G;
-#pragma unroll 1
-        for (int e = 0; e < 144; ++e) P[e] = 0.0;
-#pragma unroll
-        for (int a = 0; a < 12; ++a) P[a * 13] = p.Q[a];
-#pragma unroll 1
-        for (int i = HZ - 1; i >= 0; --i) {
-            SV B = ws + (L::o_Bm + 6 * NU * i), Rt = ws + (L::o_Rt + NU * NU * i), ri = ws + (L::o_rinv + 9 * i);
-            SV K = ws + (L::o_K + NU * 12 * i), Lc = ws + (L::o_Lc + NU * NU * i);
-            // PB = P[:, 6:12] B
-#pragma unroll 1
-            for (int r = 0; r < 12; ++r) {
-                double pr[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) pr[k] = P[r * 12 + 6 + k];
-#pragma unroll 1
-                for (int c = 0; c < NU; ++c) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) acc += pr[k] * B[k * NU + c];
-                    PB[r * NU + c] = acc;
-                }
-            }
-            // G = Rt + B' PB[6:12, :]   (lower triangle), then its Cholesky factor in place
-#pragma unroll 1
-            for (int a = 0; a < NU; ++a) {
-                double ba[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) ba[k] = B[k * NU + a];
-#pragma unroll 1
-                for (int b = 0; b <= a; ++b) {
-                    double acc = Rt[a * NU + b];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) acc += ba[k] * PB[(6 + k) * NU + b];
-                    G[a * NU + b] = acc;
-                }
-            }
-#pragma unroll 1
-            for (int j = 0; j < NU; ++j) {
-                double d = G[j * NU + j];
-#pragma unroll 1
-                for (int k = 0; k < j; ++k) d -= Lc[j * NU + k] * Lc[j * NU + k];
-                if (!(d > 0.0) || !(d < 1e300)) return false;
-                const double r = 1.0 / sqrt(d);
-                Lc[j * NU + j] = r;
-#pragma unroll 1
-                for (int a = j + 1; a < NU; ++a) {
-                    double v = G[a * NU + j];
-#pragma unroll 1
-                    for (int k = 0; k < j; ++k) v -= Lc[a * NU + k] * Lc[j * NU + k];
-                    Lc[a * NU + j] = v * r;
-                }
-            }
-            // F = PB' A  (NU x 12), K = inv(G) F
-#pragma unroll 1
-            for (int c = 0; c < NU; ++c) {
-                double f[12];
-#pragma unroll
-                for (int j = 0; j < 12; ++j) f[j] = PB[j * NU + c];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    f[6 + k] += dt * (f[0] * ri[k] + f[1] * ri[3 + k] + f[2] * ri[6 + k]);
-                    f[9 + k] += dt * f[3 + k];
-                }
-#pragma unroll
-                for (int j = 0; j < 12; ++j) F[c * 12 + j] = f[j];
-            }
-#pragma unroll 1
-            for (int j = 0; j < 12; ++j) {
-#pragma unroll 1
-                for (int a = 0; a < NU; ++a) {  // forward
-                    double v = F[a * 12 + j];
-#pragma unroll 1
-                    for (int k = 0; k < a; ++k) v -= Lc[a * NU + k] * K[k * 12 + j];
-                    K[a * 12 + j] = v * Lc[a * NU + a];
-                }
-#pragma unroll 1
-                for (int a = NU - 1; a >= 0; --a) {  // backward
-                    double v = K[a * 12 + j];
-#pragma unroll 1
-                    for (int k = a + 1; k < NU; ++k) v -= Lc[k * NU + a] * K[k * 12 + j];
-                    K[a * 12 + j] = v * Lc[a * NU + a];
-                }
-            }
-            if (i == 0) break;
-            // P <- Q + A' P A - F' K
-            congruence(P, ri);
-#pragma unroll 1
-            for (int r = 0; r < 12; ++r) {
-#pragma unroll 1
-                for (int c = 0; c <= r; ++c) {
-                    double acc = 0.5 * (P[r * 12 + c] + P[c * 12 + r]);
-#pragma unroll 1
-                    for (int a = 0; a < NU; ++a) acc -= F[a * 12 + r] * K[a * 12 + c];
-                    P[r * 12 + c] = acc;
-                    P[c * 12 + r] = acc;
-                }
-                P[r * 13] += p.Q[r];
-            }
-        }
-        return true;
-    }
-
-    // x <- inv(M) x  with the factor of the last factor() call
-    BMPC_HD void solve(SV x) {
-        if constexpr (LB == 5) {
-            solve1(x);
-            return;
-        }
-        double pv[12];
-#pragma unroll
-        for (int a = 0; a < 12; ++a) pv[a] = 0.0;
-#pragma unroll 1
-        for (int i = HZ - 1; i >= 0; --i) {
-            SV B = ws + (L::o_Bm + 6 * NU * i), ri = ws + (L::o_rinv + 9 * i), K = ws + (L::o_K + NU * 12 * i), xi = x + NU * i;
-            double t[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) t[k] = dt * (ri[k] * pv[0] + ri[3 + k] * pv[1] + ri[6 + k] * pv[2]);
-            double np[12];
-#pragma unroll
-            for (int a = 0; a < 12; ++a) np[a] = pv[a];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) np[6 + k] += t[k], np[9 + k] += dt * pv[3 + k];
-#pragma unroll 1
-            for (int c = 0; c < NU; ++c) {
-                double g = -xi[c];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) g += B[k * NU + c] * pv[6 + k];
-                xi[c] = g;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) np[j] -= K[c * 12 + j] * g;
-            }
-#pragma unroll
-            for (int a = 0; a < 12; ++a) pv[a] = np[a];
-        }
-        double z[12];
-#pragma unroll
-        for (int a = 0; a < 12; ++a) z[a] = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < HZ; ++i) {
-            SV B = ws + (L::o_Bm + 6 * NU * i), ri = ws + (L::o_rinv + 9 * i), K = ws + (L::o_K + NU * 12 * i),
-               Lc = ws + (L::o_Lc + NU * NU * i), xi = x + NU * i;
-#pragma unroll 1
-            for (int a = 0; a < NU; ++a) {
-                double v = xi[a];
-#pragma unroll 1
-                for (int k = 0; k < a; ++k) v -= Lc[a * NU + k] * xi[k];
-                xi[a] = v * Lc[a * NU + a];
-            }
-            double acc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-            for (int a = NU - 1; a >= 0; --a) {
-                double v = xi[a];
-#pragma unroll 1
-                for (int k = a + 1; k < NU; ++k) v -= Lc[k * NU + a] * xi[k];
-                xi[a] = v * Lc[a * NU + a];
-            }
-#pragma unroll 1
-            for (int a = 0; a < NU; ++a) {
-                double v = xi[a];
-#pragma unroll
-                for (int j = 0; j < 12; ++j) v += K[a * 12 + j] * z[j];
-                v = -v;
-                xi[a] = v;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) acc[k] += B[k * NU + a] * v;
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                z[a] += dt * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
-                z[3 + a] += dt * z[9 + a];
-            }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) z[6 + k] += acc[k];
-        }
-    }
-
+    // ---- backward Riccati sweep (factors  blockdiag(Rt) + B' (state cost) B  in stage-wise form) and the solves with it ----
+    BMPC_HD __forceinline__ bool factor() { return factor1(); }
+    BMPC_HD __forceinline__ void solve(SV x) { solve1(x); }
 
     // ---- LB == 5: register-blocked sweep over VIRTUAL stages of one block (5 inputs) each; cost-to-go kept as a packed
     //      lower triangle (78).  A stage with two stance feet is two virtual stages: Z = A X + B_0 u_0, then X' = Z + B_1 u_1 ----
@@ -532,7 +370,7 @@ struct LaneSolver {
 #pragma unroll
             for (int a = 0; a < 5; ++a)
 #pragma unroll
-                for (int j = 0; j < 12; ++j) np[j] -= Y[a * 12 + j] * w[a];
+                for (int j = 0; j < 12; ++j) np[j] -= Y.lds(a * 12 + j) * w[a];
 #pragma unroll
             for (int a = 0; a < 12; ++a) pv[a] = np[a];
         }
@@ -550,7 +388,7 @@ struct LaneSolver {
             for (int a = 0; a < 5; ++a) {
                 double v = xi[a];
 #pragma unroll
-                for (int j = 0; j < 12; ++j) v += Y[a * 12 + j] * z[j];
+                for (int j = 0; j < 12; ++j) v += Y.lds(a * 12 + j) * z[j];
                 t[a] = v;
             }
 #pragma unroll
@@ -814,7 +652,7 @@ struct LaneSolver {
         }
         const double mu0 = p.mu0_scale * part / (double)m;
 #pragma unroll 1
-        for (int r = 0; r < m; ++r) r_l[r] = mu0 / r_s[r];
+        for (int r = 0; r < m; ++r) r_l.sts(r, mu0 / r_s.lds(r));
 #pragma unroll 1
         for (int j = 0; j < S; ++j) {  // input maps in use, block layout [block][6][LB] (the problem's maps B0 are [stage][6][NU])
             const int st = j / NF, li = j - st * NF;
@@ -847,7 +685,6 @@ struct LaneSolver {
             part = 0.0;
 #pragma unroll 1
             for (int j = 0; j < S; ++j) {
-                const int st = j / NF, li = j - st * NF;
                 double vb[LB], gacc[LB], acc[LB * (LB + 1) / 2];
 #pragma unroll
                 for (int c = 0; c < LB; ++c) {  // the previous iteration's step is applied here (alpha_prev = 0 in the first one)
@@ -867,12 +704,12 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
-                    double s = r_s[r], l = r_l[r];
+                    double s = r_s.lds(r), l = r_l.lds(r);
                     if (alpha_prev != 0.0) {
-                        s += alpha_prev * r_p[r];
-                        l += alpha_prev * r_c[r];
-                        r_s[r] = s;
-                        r_l[r] = l;
+                        s += alpha_prev * r_p.lds(r);
+                        l += alpha_prev * r_c.lds(r);
+                        r_s.sts(r, s);
+                        r_l.sts(r, l);
                     }
                     double cb[LB];
                     crow(k, cb);
@@ -880,7 +717,7 @@ struct LaneSolver {
 #pragma unroll
                     for (int c = 0; c < LB; ++c) cu += cb[c] * vb[c];
                     const double d = l / s, rp = cu + s - rb[k];
-                    r_p[r] = rp;
+                    r_p.sts(r, rp);
                     const double w = d * rp - l;
                     part += s * l;
 #pragma unroll
@@ -918,11 +755,11 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
-                    const double sr = r_s[r], lr = r_l[r];
-                    const double dsa = -r_p[r] - cdotr(k, vb);
+                    const double sr = r_s.lds(r), lr = r_l.lds(r);
+                    const double dsa = -r_p.lds(r) - cdotr(k, vb);
                     const double dla = -lr - (lr / sr) * dsa;
                     ratio = fmaxf(ratio, fmaxf(sratio(dsa, sr), sratio(dla, lr)));
-                    r_c[r] = dsa * dla;
+                    r_c.sts(r, dsa * dla);
                     part += dsa * dla;
                 }
             }
@@ -940,8 +777,8 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
-                    const double wc = (r_c[r] - tgt) / r_s[r];
-                    r_c[r] = wc;
+                    const double wc = (r_c.lds(r) - tgt) / r_s.lds(r);
+                    r_c.sts(r, wc);
                     double cb[LB];
                     crow(k, cb);
 #pragma unroll
@@ -962,12 +799,12 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int k = 0; k < mb; ++k) {
                     const int r = j * mb + k;
-                    const double sr = r_s[r], lr = r_l[r];
-                    const double ds = -r_p[r] - cdotr(k, vb);
-                    const double dl = -lr - r_c[r] - (lr / sr) * ds;
+                    const double sr = r_s.lds(r), lr = r_l.lds(r);
+                    const double ds = -r_p.lds(r) - cdotr(k, vb);
+                    const double dl = -lr - r_c.lds(r) - (lr / sr) * ds;
                     ratio = fmaxf(ratio, fmaxf(sratio(ds, sr), sratio(dl, lr)));
-                    r_p[r] = ds;
-                    r_c[r] = dl;
+                    r_p.sts(r, ds);
+                    r_c.sts(r, dl);
                 }
             }
             double a2 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
@@ -979,10 +816,10 @@ struct LaneSolver {
                 const double at = fmin(1.0, 1.5 * a2 + 0.1);
 #pragma unroll 1
                 for (int r = 0; r < m; ++r) {
-                    const double v = (r_s[r] + at * r_p[r]) * (r_l[r] + at * r_c[r]);
+                    const double v = (r_s.lds(r) + at * r_p.lds(r)) * (r_l.lds(r) + at * r_c.lds(r));
                     double vt = fmin(fmax(v, 0.1 * tgt), 10.0 * tgt) - v;
                     vt = fmax(vt, -10.0 * tgt);
-                    r_w[r] = -vt / r_s[r];
+                    r_w[r] = -vt / r_s.lds(r);
                 }
                 gather(r_w, xv, 0.0, xv);
                 solve(xv);
@@ -996,9 +833,9 @@ struct LaneSolver {
                     for (int k = 0; k < mb; ++k) {
                         const int r = j * mb + k;
                         const double cx = cdotr(k, vb);
-                        const double ds = r_p[r] - cx;
-                        const double dl = r_c[r] + r_d[r] * cx - r_w[r];
-                        ratio = fmaxf(ratio, fmaxf(sratio(ds, r_s[r]), sratio(dl, r_l[r])));
+                        const double ds = r_p.lds(r) - cx;
+                        const double dl = r_c.lds(r) + r_d[r] * cx - r_w[r];
+                        ratio = fmaxf(ratio, fmaxf(sratio(ds, r_s.lds(r)), sratio(dl, r_l.lds(r))));
                     }
                 }
                 const double a3 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
@@ -1013,8 +850,8 @@ struct LaneSolver {
                         for (int k = 0; k < mb; ++k) {
                             const int r = j * mb + k;
                             const double cx = cdotr(k, vb);
-                            r_p[r] -= cx;
-                            r_c[r] += r_d[r] * cx - r_w[r];
+                            r_p.sts(r, r_p.lds(r) - (cx));
+                            r_c.sts(r, r_c.lds(r) + (r_d[r] * cx - r_w[r]));
                         }
                     }
 #pragma unroll 1
