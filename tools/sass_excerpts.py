@@ -31,7 +31,7 @@ for name, ins in funcs.items():
     print(f"| `{d}` | {len(ins)} | {len(ins) * 16 / 1024:.0f} | {c['DFMA']} | {c['DMUL'] + c['DADD']} | {c['LDS']} | {c['STS']} | "
           f"{c['LDG'] + c['LD']} | {c['STG'] + c['ST']} | {c['SHFL']} | {c['UBLKCP']} | {c['SYNCS']} | {c['BAR']} | {c['MUFU']} |")
 # excerpts from the shipped walking-class kernel
-key = [n for n in funcs if "Li10ELi10ELi5ELi32ELi5ELb0" in n][0]
+key = ([n for n in funcs if "Li10ELi10ELi5ELi32ELi8ELb0" in n] + [n for n in funcs if "Li10ELi10ELi5ELi32E" in n])[0]
 ins = funcs[key]
 print(f"\n## Excerpts from `{demangle(key).split('(')[0]}` (walking class)\n")
 idx = [i for i, (_, t) in enumerate(ins) if "UBLKCP" in t]
@@ -54,3 +54,28 @@ print("(`tile_factor`, bmpc_tick.cuh): 10 `LDS.64` of one column of each panel t
 for a, t in ins[bi: bi + W]:
     print(f"/*{a:05x}*/ {t}")
 print("```")
+
+# lane-per-robot kernel: densest DFMA window (the rank-5 update of the packed cost-to-go in the register-blocked sweep) and the
+# streaming accesses of the stored factor
+lk = [n for n in funcs if "lane_tick_kernelILi10ELi1ELi5" in n]
+if lk:
+    ins = funcs[lk[0]]
+    print(f"\n## Excerpts from `{demangle(lk[0]).split('(')[0]}` (lane-per-robot kernel, walking class; `<10, 2, 5>` is the same code over 20 virtual stages)\n")
+    isf = [1 if "DFMA" in t else 0 for _, t in ins]
+    best, bi, s2 = -1, 0, sum(isf[:W])
+    for i in range(len(ins) - W):
+        if s2 > best:
+            best, bi = s2, i
+        s2 += isf[i + W] - isf[i]
+    print(f"Densest FP64 window ({best} DFMA in {W} instructions): register-resident operands, one thread = one robot (no shuffles, no barriers, no shared memory):\n\n```")
+    for a, t in ins[bi: bi + W]:
+        print(f"/*{a:05x}*/ {t}")
+    print("```\n")
+    cs = [i for i, (_, t) in enumerate(ins) if ".EF" in t or "EVICT_FIRST" in t.upper() or ".CS" in t.upper()]
+    c = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0] for _, t in ins)
+    print("Global accesses go to the lane-interleaved workspace (element i of lane l at `ws[i*32 + l]`: one 256-byte line pair per warp access); "
+          "the stored factor and the row arrays use the streaming (evict-first) forms. Global/local memory opcodes of the kernel:\n\n```")
+    for op, n in sorted(c.items(), key=lambda kv: -kv[1]):
+        if op.split(".")[0] in ("LDG", "STG", "LD", "ST", "LDL", "STL", "LDC", "LDCU"):
+            print(f"{n:6d}  {op}")
+    print("```")
