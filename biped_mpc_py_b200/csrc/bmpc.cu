@@ -247,6 +247,19 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
                 rc = setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], sms, mb) ||
                      setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], sms, mb) ||
                      setup_variant<30, 60, 5, 256, 1, true>(h->fallback, sms, mb);
+            // lane-per-robot front end at h = 30 (same horizon-templated source).  The warp-per-robot h = 30 kernels are much
+            // slower per robot than the h = 10 ones, so the size gates are lower: measured at 131,072 instances the walking class
+            // (111 k robots) takes 258 ms on the lane kernel against 869 ms.
+            const char* ela30 = getenv("BMPC_LANE");
+            const int lane_mode30 = ela30 ? atoi(ela30) : 2;
+            if (!rc && lane_mode30 != 0) {
+                const char* elm = getenv("BMPC_LANE_MIN");
+                h->lane_min = elm ? atoi(elm) : 6144;
+                h->lane[0].min_count = elm ? atoi(elm) : 12288;
+                h->lane[1].min_count = elm ? atoi(elm) : 6144;
+                rc = setup_lane<30, 1, 5>(h->lane[0], sms, 0, max_batch);
+                if (!rc && lane_mode30 >= 2) rc = setup_lane<30, 2, 5>(h->lane[1], sms, 0, max_batch);
+            }
         }
     } else if (h->dp.LB == 5) {
 #ifdef BMPC_EXPERIMENTS

@@ -106,3 +106,28 @@ def test_h30_unpinned_limit_set_lb6():
         assert np.abs(out["controls"][i] - ct).max() / max(1.0, np.abs(ct).max()) <= U_RTOL, i
         assert np.abs(out["tau"][i] - tau).max() <= TAU_ATOL, i
     s.close()
+
+
+def test_h30_lane_per_robot_front_end_matches_warp_kernels(monkeypatch):
+    """h = 30 through the lane-per-robot kernels (size gates removed) against the warp-per-robot kernels alone."""
+    import numpy as np
+    from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
+    n = 512
+    mpc, biped = MPC(h=30), Biped()
+    b = synth.make_batch(n, shard_index=31, mpc=mpc, biped=biped, extend=True)
+    args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+    monkeypatch.setenv("BMPC_LANE", "0")
+    ref_solver = BatchedMPC(mpc, biped, max_batch=n, extend_gait=True)
+    ref = ref_solver.step_host(*args, phase_k=b["phase_k"])
+    ref_solver.close()
+    monkeypatch.setenv("BMPC_LANE", "2")
+    monkeypatch.setenv("BMPC_LANE_MIN", "1")
+    lane_solver = BatchedMPC(mpc, biped, max_batch=n, extend_gait=True)
+    out = lane_solver.step_host(*args, phase_k=b["phase_k"])
+    lane_solver.close()
+    assert (ref["status"] == 0).all() and (out["status"] == 0).all()
+    assert out["iters"].mean() > ref["iters"].mean()  # the lane kernel has no Gondzio corrector: it really ran
+    scale = np.maximum(1.0, np.abs(ref["controls"]).reshape(n, -1).max(axis=1))
+    du = np.abs(out["controls"] - ref["controls"]).reshape(n, -1).max(axis=1) / scale
+    assert du.max() <= 1e-6, du.max()
+    assert np.abs(out["tau"] - ref["tau"]).max() <= 1e-6
