@@ -32,18 +32,18 @@ def lane_lib():
     return ctypes.CDLL(OUT)
 
 
-def _run(lib, mpc, biped, x_fb, t, foot, contact, q, qd, pf_w):
+def _run(lib, mpc, biped, x_fb, t, foot, contact, q, qd, pf_w, phase_k=None):
     from biped_mpc_py_b200.gait import gait_phase
     from biped_mpc_py_b200.params import pack_params
-    n = x_fb.shape[0]
-    P = pack_params(mpc, biped)
+    n, h = x_fb.shape[0], int(mpc.h)
+    P = pack_params(mpc, biped, extend_gait=(h != 10))
     c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
     x_fb, t, foot, q, qd, pf_w = c(x_fb), c(t), c(foot), c(q), c(qd), c(pf_w)
     contact = c(contact, np.uint8)
-    phase_k = c(gait_phase(t, mpc) % int(mpc.h), np.int32)
-    out = dict(controls=np.zeros((n, 10, 12)), states=np.zeros((n, 10, 13)), tau=np.zeros((n, 10)),
-               status=np.full(n, -7, np.int32), iters=np.zeros(n, np.int32), fric=np.zeros((n, 10), np.uint8),
-               resid=np.zeros((n, 2)), ws_mask=np.zeros((n, 20), np.int32))
+    phase_k = c(gait_phase(t, mpc) % h if phase_k is None else phase_k, np.int32)
+    out = dict(controls=np.zeros((n, h, 12)), states=np.zeros((n, h, 13)), tau=np.zeros((n, 10)),
+               status=np.full(n, -7, np.int32), iters=np.zeros(n, np.int32), fric=np.zeros((n, h), np.uint8),
+               resid=np.zeros((n, 2)), ws_mask=np.zeros((n, 2 * h), np.int32))
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib.lane_host_tick(ctypes.byref(P), n, p(x_fb), p(phase_k), p(t), p(foot), p(contact), p(q), p(qd), p(pf_w),
                             p(out["controls"]), p(out["states"]), p(out["tau"]), p(out["status"]), p(out["iters"]),
@@ -133,3 +133,19 @@ def test_lane_solver_randomised_parameter_sets(lane_lib):
             _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, biped, b["contact"][i])
             assert np.abs(out["controls"][i] - u).max() / max(1.0, np.abs(u).max()) <= 1e-5, (trial, i)
     assert accepted >= 4
+
+
+def test_lane_solver_horizon_30(lane_lib):
+    """The same horizon-templated source at h = 30 (periodic gait extension for the walking robots)."""
+    from biped_mpc_py_b200 import synth
+    from oracle import reference_mpc as rm
+    mpc, biped = rm.MPCParams(h=30), rm.BipedParams()
+    n = 48
+    b = synth.make_batch(n, shard_index=5, mpc=mpc, biped=biped, extend=True)
+    out = _run(lane_lib, mpc, biped, b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"], phase_k=b["phase_k"])
+    assert (out["status"] == 0).mean() >= 0.9 and np.isin(out["status"], (0, 1)).all()
+    ok = np.nonzero(out["status"] == 0)[0]
+    picks = [int(ok[0])] + [int(j) for j in ok if b["gait"][j] == 0][:1]
+    for i in picks:
+        _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, biped, b["contact"][i], extend=True)
+        assert np.abs(out["controls"][i] - u).max() / max(1.0, np.abs(u).max()) <= 1e-5, i
