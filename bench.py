@@ -219,7 +219,7 @@ def other_configs(torch, dev, local_rank, rank, world, barrier, max_over_ranks, 
         return max_over_ranks(e0.elapsed_time(e1)) / reps, r
 
     # configs[3]: horizon 30 (periodic gait extension for the walking instances; standing is reference-defined)
-    n30 = 8192
+    n30 = 65536  # large enough for the lane-per-robot kernels (size gates 12,288 walking / 6,144 standing robots at h = 30)
     mpc30 = MPC(h=30)
     b = synth.make_batch(n30, shard_index=1000 + rank, mpc=mpc30, extend=True)
     s30 = BatchedMPC(mpc30, Biped(), max_batch=n30, device=local_rank, extend_gait=True)
