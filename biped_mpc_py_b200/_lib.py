@@ -10,7 +10,7 @@ from .params import BmpcParams
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbiped_mpc_b200.so")
 
 EXPORTS = ["bmpc_create", "bmpc_destroy", "bmpc_step", "bmpc_solve", "bmpc_lowlevel", "bmpc_foot_positions", "bmpc_rollout", "bmpc_warm_start",
-           "bmpc_debug_assemble", "bmpc_launch_count", "bmpc_enable_timing", "bmpc_last_timing", "bmpc_measure_fma_peak", "bmpc_last_error",
+           "bmpc_debug_assemble", "bmpc_set_option", "bmpc_launch_count", "bmpc_enable_timing", "bmpc_last_timing", "bmpc_measure_fma_peak", "bmpc_last_error",
            "bmpc_abi_version"]
 
 _lib = None
@@ -25,7 +25,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("BMPC_LIB_PATH", LIB_PATH)  # alternative builds of the same sources (compiler-flag experiments)
+    path = LIB_PATH
     if not os.path.exists(path):
         raise LibraryMissing(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -51,6 +51,8 @@ def load():
     lib.bmpc_warm_start.restype = c_int
     lib.bmpc_debug_assemble.argtypes = [c_void_p] + [vp] * 7 + [vp]
     lib.bmpc_debug_assemble.restype = c_int
+    lib.bmpc_set_option.argtypes = [c_void_p, c_char_p, c_int]
+    lib.bmpc_set_option.restype = c_int
     lib.bmpc_launch_count.argtypes = [c_void_p]
     lib.bmpc_launch_count.restype = c_int64
     lib.bmpc_enable_timing.argtypes = [c_void_p, c_int]

@@ -81,6 +81,11 @@ class BatchedMPC:
     def launch_count(self) -> int:
         return int(self._lib.bmpc_launch_count(self._h))
 
+    def set_option(self, name: str, value: int):
+        """Dispatch tunables of include/biped_mpc_b200.h::bmpc_set_option (``lane_mode``, ``lane_min``,
+        ``lane_ctas_per_sm``, ``lane_warps``, ``lowlat``); every setting returns the same certified optimum."""
+        _lib.check(self._lib.bmpc_set_option(self._h, name.encode(), int(value)))
+
     def warm_start(self, on: bool = True):
         """Warm start across consecutive ``step`` / ``solve`` calls of a caller-owned control loop: robot i of the
         batch must be the same robot one tick later.  Same certified optimum as the cold solve, ~3x faster ticks."""

@@ -8,11 +8,10 @@
 #include <string.h>
 
 #include <algorithm>
-#include <mutex>
 #include <string>
 
 #include "../../include/biped_mpc_b200.h"
-#include "bmpc_lane.cuh"
+#include "bmpc_lane_api.h"
 #include "bmpc_presolve.h"
 #include "bmpc_rollout.cuh"
 #include "bmpc_small.cuh"
@@ -36,15 +35,15 @@ int fail(const std::string& msg) {
 
 typedef void (*TickKernel)(const DevParams, const IoPtrs, const int*, const int*, double*);
 
-typedef void (*LaneKernel)(const DevParams, const IoPtrs, const int*, const int*, int*, double*, int);
-
 // lane-per-robot front end of one class (bmpc_lane.cuh): what it certifies is done, the rest goes to the class's Variant
 struct LaneVariant {
     LaneKernel fn = nullptr;
     int grid = 0;
+    int threads = 0;         // 32 robots per warp
+    size_t smem = 0;         // dynamic shared memory per CTA: the packed cost-to-go of its robots
     size_t ws_doubles = 0;
     int min_count = 0;       // classes smaller than this stay on the warp-per-robot kernel (decided on the device)
-    double* d_ws = nullptr;  // [warps][total][32] lane-interleaved work arrays
+    double* d_ws = nullptr;  // [warps][blocks][record][32] lane-interleaved block records
 };
 
 struct Variant {
@@ -67,8 +66,14 @@ struct bmpc_handle {
     DevParams dp;
     Variant bucket[2];
     Variant lowlat;           // walking class for small batches: 128 threads per robot (latency, not throughput), or empty
-    LaneVariant lane[2];      // h = 10, LB = 5: lane-per-robot front end per class (batches >= lane_min), or empty
+    LaneVariant lane[2];      // LB = 5, mx pinned: lane-per-robot front end per class (batches >= lane_min), or empty
     int lane_min = 0;
+    // tunables (bmpc_set_option); -1 = the built-in default
+    int opt_lane_mode = -1;        // 2 both classes, 1 walking class only, 0 warp-per-robot kernels only
+    int opt_lane_min = -1;         // overrides the three size gates
+    int opt_lane_ctas_per_sm = -1; // resident CTAs per SM of the lane kernels
+    int opt_lane_warps = -1;       // warps (32 robots each) per CTA
+    int opt_lowlat = -1;           // 0 disables the 128-thread walking variant for batches <= 8
     Variant fallback;         // dense re-solve of instances the stage-wise class-1 kernel did not certify (h = 30), or empty
     int* d_lists = nullptr;   // [5][max_batch]: two classes, the h = 30 fallback list, the two lane-residual lists
     int* d_counts = nullptr;  // [16]: list count i has its dynamic work counter at i + 3 (lists 0-2 and 6-7); 12, 13 lane slice counters
@@ -103,7 +108,9 @@ int setup_variant(Variant& v, int num_sms, int mb) {
     using L = TickLayout<HZ, SMAX, LB, MG, RIC>;
     v.fn = mpc_tick2_kernel<HZ, SMAX, LB, NT, NW, MG, RIC>;
     v.smem = L::bytes(mb) * NW + 16;  // + the CTA-wide lockstep mbarrier
+#ifdef BMPC_EXPERIMENTS
     if (const char* ep = getenv("BMPC_PAD_SMEM")) v.smem += (size_t)atoi(ep);  // occupancy experiments only
+#endif
     v.threads = NT * NW;
     v.per_cta = NW;
     v.scratch_doubles = L::g_total;
@@ -116,15 +123,20 @@ int setup_variant(Variant& v, int num_sms, int mb) {
     return 0;
 }
 
-template <int HZ, int NF, int LB>
-int setup_lane(LaneVariant& v, int num_sms, int ctas_per_sm, int max_batch) {
-    v.fn = lane_tick_kernel<HZ, NF, LB>;
+int setup_lane(LaneVariant& v, const DevParams& d, int nf, int num_sms, int ctas_per_sm, int warps, int max_batch) {
+    const LaneKernelInfo k = d.h == 30 ? lane_kernel_info_h30(nf, lane_rowmask(d)) : lane_kernel_info_h10(nf, lane_rowmask(d));
+    if (!k.fn) return fail("no lane kernel for this horizon");
+    if (v.d_ws) cudaFree(v.d_ws), v.d_ws = nullptr;
+    v.fn = k.fn;
+    v.threads = 32 * warps;
+    v.smem = sizeof(double) * (size_t)k.smem_doubles * 32 * warps;
+    CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, 128, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, v.threads, v.smem));
     if (per_sm < 1) return fail("lane kernel does not fit on an SM");
     if (ctas_per_sm > 0) per_sm = std::min(per_sm, ctas_per_sm);
-    v.grid = std::min(per_sm * num_sms, (max_batch + 127) / 128);
-    v.ws_doubles = (size_t)LaneL<HZ, NF, LB>::total * 32 * 4 * (size_t)v.grid;  // allocated on first use (throughput batches only)
+    v.grid = std::min(per_sm * num_sms, (max_batch + v.threads - 1) / v.threads);
+    v.ws_doubles = (size_t)k.ws_doubles * 32 * warps * (size_t)v.grid;  // allocated on first use (throughput batches only)
     return 0;
 }
 
@@ -148,7 +160,7 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         // real-time use (N = 1 .. 8): every walking robot gets a whole 128-thread CTA (0.26 ms instead of 0.32 ms for one
         // robot end to end).  Same optimum, but reductions run in a different order, so results of batches <= 8 may
         // differ in the last bits from the throughput kernel; every larger batch is bit-identical under any split.
-        const Variant& v = (b == 0 && h->lowlat.fn && n <= 8) ? h->lowlat : h->bucket[b];
+        const Variant& v = (b == 0 && h->lowlat.fn && h->opt_lowlat != 0 && n <= 8) ? h->lowlat : h->bucket[b];
         // persistent thread groups: as many as fit on the device, each strides over its bucket's work list
         const int grid = (std::min(n, v.resident) + v.per_cta - 1) / v.per_cta;
         const int* list = h->d_lists + (size_t)b * h->max_batch;
@@ -158,8 +170,9 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
             // certify (status 1) are collected and solved by the warp-per-robot kernel below
             int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
             if (!h->lane[b].d_ws) CUDA_TRY(cudaMalloc(&h->lane[b].d_ws, sizeof(double) * h->lane[b].ws_doubles));
-            h->lane[b].fn<<<std::min(h->lane[b].grid, (n + 127) / 128), 128, 0, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b, h->lane[b].d_ws,
-                                                                                       h->lane[b].min_count);
+            const LaneVariant& lv = h->lane[b];
+            lv.fn<<<std::min(lv.grid, (n + lv.threads - 1) / lv.threads), lv.threads, lv.smem, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b,
+                                                                                                      lv.d_ws, lv.min_count);
             collect_or_all_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b, h->lane[b].min_count);
             list = rlist, cnt = h->d_counts + 6 + b;
             h->launches += 2;
@@ -180,6 +193,37 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     h->launches += 3;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// Lane-per-robot front end (bmpc_lane.cuh) for throughput batches (n >= lane_min): one THREAD per robot, 32 robots per
+// instruction; whatever it does not certify falls through to the warp-per-robot kernel of the class.  It needs the reference's
+// limit structure (five free components, mx pinned: tau_max[0] = tau_min[0], MPC.py:47).
+// Size gates: a 32-robot slice takes a fixed time however small the batch, so the front end pays only when a class can
+// occupy the machine; the class sizes are only known on the device, so the lane kernel itself returns at once for a small
+// class and collect_or_all_kernel passes the whole list on.
+int setup_lanes(bmpc_handle* h) {
+    for (int b = 0; b < 2; ++b) {
+        if (h->lane[b].d_ws) cudaFree(h->lane[b].d_ws);
+        h->lane[b] = LaneVariant();
+    }
+    h->lane_min = 0;
+    const DevParams& d = h->dp;
+    if (d.LB != 5 || d.npinned != 1 || d.pinned[0] != 3 || d.mb > 16) return 0;
+    const int mode = h->opt_lane_mode >= 0 ? h->opt_lane_mode : 2;
+    if (mode == 0) return 0;
+    const int warps = h->opt_lane_warps > 0 ? h->opt_lane_warps : 4;
+    const int ctas = h->opt_lane_ctas_per_sm > 0 ? h->opt_lane_ctas_per_sm : 0;
+    const bool h30 = d.h == 30;
+    h->lane_min = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 6144 : 20480);
+    h->lane[0].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 12288 : 49152);
+    h->lane[1].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 6144 : 20480);
+    int rc = setup_lane(h->lane[0], d, 1, h->num_sms, ctas, warps, h->max_batch);
+    if (!rc && mode >= 2) {
+        const int mc = h->lane[1].min_count;
+        rc = setup_lane(h->lane[1], d, 2, h->num_sms, ctas, warps, h->max_batch);
+        h->lane[1].min_count = mc;
+    }
+    return rc;
 }
 
 }  // namespace
@@ -247,19 +291,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
                 rc = setup_variant<30, 30, 5, 128, 1, false, true>(h->bucket[0], sms, mb) ||
                      setup_variant<30, 60, 5, 128, 1, false, true>(h->bucket[1], sms, mb) ||
                      setup_variant<30, 60, 5, 256, 1, true>(h->fallback, sms, mb);
-            // lane-per-robot front end at h = 30 (same horizon-templated source).  The warp-per-robot h = 30 kernels are much
-            // slower per robot than the h = 10 ones, so the size gates are lower: measured at 131,072 instances the walking class
-            // (111 k robots) takes 258 ms on the lane kernel against 869 ms.
-            const char* ela30 = getenv("BMPC_LANE");
-            const int lane_mode30 = ela30 ? atoi(ela30) : 2;
-            if (!rc && lane_mode30 != 0) {
-                const char* elm = getenv("BMPC_LANE_MIN");
-                h->lane_min = elm ? atoi(elm) : 6144;
-                h->lane[0].min_count = elm ? atoi(elm) : 12288;
-                h->lane[1].min_count = elm ? atoi(elm) : 6144;
-                rc = setup_lane<30, 1, 5>(h->lane[0], sms, 0, max_batch);
-                if (!rc && lane_mode30 >= 2) rc = setup_lane<30, 2, 5>(h->lane[1], sms, 0, max_batch);
-            }
+            if (!rc) rc = setup_lanes(h);
         }
     } else if (h->dp.LB == 5) {
 #ifdef BMPC_EXPERIMENTS
@@ -273,28 +305,8 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         else
 #endif
             if (!rc) rc = setup_variant<10, 20, 5, 128, 1>(h->bucket[1], sms, mb);  // standing: one 128-thread CTA per robot
-        // Lane-per-robot front end (bmpc_lane.cuh) for throughput batches (n >= lane_min): one THREAD per robot, 32 robots per
-        // instruction; whatever it does not certify falls through to the warp-per-robot kernel of the class.  Measured per
-        // 262,144-robot batch: walking class 70 ms vs 92 ms, standing class 32 ms vs 57 ms.
-        // BMPC_LANE: 2 (default) both classes, 1 walking class only, 0 warp-per-robot kernels only.
-        const char* ela = getenv("BMPC_LANE");
-        const int lane_mode = ela ? atoi(ela) : 2;
-        if (!rc && lane_mode != 0) {
-            // Size gates.  One 32-robot slice takes ~20 ms however small the batch, so the front end pays only when a class fills
-            // the machine: measured crossover ~46 k walking / ~16 k standing robots (65,536-robot batch: 18.9 vs 23.0 ms walking,
-            // 23.5 vs 14.3 ms standing; 262,144: 69 vs 92 and 31 vs 57 ms).  The class sizes are only known on the device, so the
-            // lane kernel itself returns at once for a small class and collect_or_all_kernel passes the whole list on.
-            // BMPC_LANE_MIN overrides all three gates (tests use 1).
-            const char* elm = getenv("BMPC_LANE_MIN");
-            h->lane_min = elm ? atoi(elm) : 20480;
-            h->lane[0].min_count = elm ? atoi(elm) : 49152;
-            h->lane[1].min_count = elm ? atoi(elm) : 20480;
-            const char* elc = getenv("BMPC_LANE_CTAS");  // CTAs (4 warps = 128 robots each) per SM
-            rc = setup_lane<10, 1, 5>(h->lane[0], sms, elc ? atoi(elc) : 0, max_batch);
-            if (!rc && lane_mode >= 2) rc = setup_lane<10, 2, 5>(h->lane[1], sms, elc ? atoi(elc) : 0, max_batch);
-        }
-        const char* ell = getenv("BMPC_LOWLAT");  // 0 disables the low-latency walking variant for batches <= 8
-        if (!rc && !(ell && atoi(ell) == 0)) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, sms, mb);
+        if (!rc) rc = setup_lanes(h);
+        if (!rc) rc = setup_variant<10, 10, 5, 128, 1>(h->lowlat, sms, mb);  // batches <= 8: 128 threads per walking robot
     } else {
         rc = setup_variant<10, 10, 6, 32, 6>(h->bucket[0], sms, mb) || setup_variant<10, 20, 6, 128, 1>(h->bucket[1], sms, mb);
     }
@@ -488,6 +500,22 @@ int bmpc_debug_assemble(bmpc_handle* h, const double* x_fb, const int32_t* phase
     if (rc) return rc;
     if (e != cudaSuccess) return fail(std::string("debug kernel: ") + cudaGetErrorString(e));
     return 0;
+}
+
+int bmpc_set_option(bmpc_handle* h, const char* name, int value) {
+    if (!h || !name) return fail("bmpc_set_option: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const std::string k(name);
+    if (k == "lane_mode") h->opt_lane_mode = value;
+    else if (k == "lane_min") h->opt_lane_min = value;
+    else if (k == "lane_ctas_per_sm") h->opt_lane_ctas_per_sm = value;
+    else if (k == "lane_warps") h->opt_lane_warps = value;
+    else if (k == "lowlat") { h->opt_lowlat = value; return 0; }
+    else if (k == "lane_prefetch") { h->dp.lane_prefetch = value != 0; return 0; }
+    else if (k == "lane_sync") { h->dp.lane_sync = value; return 0; }
+    else return fail("bmpc_set_option: unknown option '" + k + "'");
+    CUDA_TRY(cudaDeviceSynchronize());  // the workspace of the lane kernels is re-sized
+    return setup_lanes(h);
 }
 
 int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }

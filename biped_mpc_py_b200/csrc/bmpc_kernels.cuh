@@ -20,6 +20,7 @@ enum RowKind { ROW_LO = 0, ROW_HI = 1, ROW_FRIC = 2, ROW_LINE = 3 };
 
 struct DevParams {
     int h, extend, LB, mb, npinned, max_iter, gondzio, warm_rounds, polish_rounds, lock_mode;
+    int lane_prefetch, lane_sync;  // lane-per-robot kernels: bulk L2 prefetch of the next block record; lockstep of the warps of a CTA (bmpc_set_option)
     int comps[6];
     int pinned[6];
     int row_kind[MAXROWS];
@@ -169,7 +170,7 @@ BMPC_HD __forceinline__ void leg_jacobian(const double* q, double side, double* 
 }
 
 // tau_leg[5] for one leg.  R = eul2rotm(x_fb[0:3]); u = [f1,f2,m1,m2] first-stage input.
-BMPC_HD __noinline__ void lowlevel_leg(const DevParams& p, const double* x_fb, double t, const double* pf_w,
+BMPC_HD __forceinline__ void lowlevel_leg_inl(const DevParams& p, const double* x_fb, double t, const double* pf_w,
                                     const double* q, const double* qd, const double* R, int leg, double c_leg,
                                     const double* u, double* tau_leg) {
     const double side = (leg == 0) ? 1.0 : -1.0;
@@ -221,6 +222,14 @@ BMPC_HD __noinline__ void lowlevel_leg(const DevParams& p, const double* x_fb, d
         for (int a = 0; a < 3; ++a) sw += J[a * 5 + c] * fs[a];
         tau_leg[c] = st * c_leg + sw * -(c_leg - 1.0);
     }
+}
+
+// out-of-line copy for the kernels where code size matters more than the call (taking the address of the kernel
+// parameter block, however, turns every later parameter read into a generic load: the lane kernels use the inline form)
+BMPC_HD inline __noinline__ void lowlevel_leg(const DevParams& p, const double* x_fb, double t, const double* pf_w,
+                                    const double* q, const double* qd, const double* R, int leg, double c_leg,
+                                    const double* u, double* tau_leg) {
+    lowlevel_leg_inl(p, x_fb, t, pf_w, q, qd, R, leg, c_leg, u, tau_leg);
 }
 
 // closed-form foot position in the hip frame (MPC.py:367-404)

@@ -1,17 +1,29 @@
-// Lane-per-robot MPC tick: ONE THREAD solves one robot, 32 robots per warp execute the same instruction stream.
+// Lane-per-robot MPC tick (second generation): ONE THREAD solves one robot, 32 robots per warp share every instruction.
 //
-// Why: the warp-per-robot kernel (bmpc_tick.cuh) is bound by instruction delivery — every warp walks a 40 KB loop at
-// its own position for one 50-variable problem, ~12 issued warp instructions per useful FP64 FMA lane-op
-// (profiles/r1_summary.md).  Here an instruction serves 32 robots, there is no cross-lane communication and no
-// barrier, and the linear algebra is the stage-wise (Riccati) form of the same QP: the contact-reduced problem is an
-// LQR problem  X_i = A_i X_{i-1} + B_i u_i + c_i  (MPC.py:165-184, 206-214) with block-diagonal input weights, so a
-// backward sweep over the 12x12 cost-to-go factors  M = Hc + blockdiag(Cb' D Cb)  in O(h) and Hc is never formed.
-// Same algorithm as the tick kernel otherwise (Mehrotra + Gondzio interior point to a loose target, active-set polish,
-// KKT certificate; the per-block null-space / multiplier checks are the SAME functions, bmpc_polish.cuh), written as
-// plain scalar C++ so that the identical source is unit-tested on the CPU (tests/lane_host.cu) against the oracle.
+// The linear algebra is the stage-wise (Riccati) form of the contact-reduced QP: the problem is an LQR problem
+//   X_v = A_v X_{v-1} + B_v u_v + c_v   (MPC.py:165-184, 206-214)
+// over VIRTUAL stages v = one stance foot-stage block of 5 free inputs [fx fy fz my mz] (mx is pinned by tau_max[0] =
+// tau_min[0], MPC.py:47); a stage with two stance feet is two virtual stages (Z = A X + B_0 u_0, then X' = Z + B_1 u_1).
+// A backward sweep over the 12x12 cost-to-go factors  M = Hc + blockdiag(C' D C)  in O(h); Hc is never formed.
 //
-// Per-robot work arrays live in a global workspace interleaved by lane (element i of lane l at ws[i*32 + l]: every
-// access of a warp is one fully used 256-byte line pair); on the host the stride is 1.
+// What bounds a kernel of this shape is the per-robot state (32 robots per warp), so everything here is built around
+// keeping that state small and touching it as few times as possible:
+//   * the inequality rows are STRUCTURAL code (box rows touch one component, friction rows two; only the two line-foot
+//     rows, MPC.py:253-271, are per-robot vectors, kept in registers): no per-thread matrices, no local memory;
+//   * per block only the iterate (u, s, lam), the two step vectors, the stationarity residual and the stage factor
+//     (Y = inv(L) F, L) are stored; everything else about the rows (residuals, affine and corrector terms, the step in s
+//     and lam) is recomputed from those where it is used, with one fast reciprocal per row;
+//   * one interior-point iteration is FOUR sweeps over the block records, in alternating directions so that the turn-around
+//     block is still in cache:  (A) backward: apply the previous step, barrier weights, right-hand side, stage factor and
+//     the backward half of the predictor solve, fused;  (B) forward half of the predictor + affine step statistics;
+//     (C) backward: corrector right-hand side + backward half of its solve;  (D) forward half + step length, the
+//     complementarity after the step and the convergence test;
+//   * the 12x12 cost-to-go (packed lower triangle, 78 doubles) lives in SHARED memory, lane-interleaved (conflict-free
+//     LDS.64); the record of block v of the 32 robots of a warp is one contiguous 41 KB panel of the global workspace
+//     (element i of lane l at ws[(v*REC + i)*32 + l]), so every access is a fully used 256-byte line pair.
+// Same algorithm otherwise as the warp-per-robot kernel (Mehrotra predictor-corrector to a loose target, active-set
+// polish with the SAME per-block null-space / multiplier functions of bmpc_polish.cuh, KKT certificate), written as plain
+// scalar C++ so that the identical source is unit-tested on the CPU (tests/lane_host.cu) against the oracle.
 // A robot this path does not certify keeps status 1 and is re-solved by the warp-per-robot kernels (bmpc.cu).
 #pragma once
 #include "bmpc_kernels.cuh"
@@ -25,97 +37,303 @@ namespace bmpc {
 #define BMPC_LS 1
 #endif
 
-struct SV {  // strided view of one lane's slice of the workspace
+// address-space hints: the views are plain pointers inside a struct, which hides from the compiler that the workspace is
+// global and the cost-to-go shared memory (generic LD/ST instead of LDG/STG and LDS/STS)
+#ifdef __CUDA_ARCH__
+#define BMPC_ASSUME_SPACES()                  \
+    __builtin_assume(__isGlobal(ws.p));       \
+    __builtin_assume(__isShared(Ps.p))
+#else
+#define BMPC_ASSUME_SPACES()
+#endif
+
+// compiler-only barrier: stops the compiler from keeping shared-memory values (the cost-to-go) in registers from one phase
+// of a stage to the next, which costs more in spills than the re-read
+#ifdef __CUDA_ARCH__
+#define BMPC_CBAR() asm volatile("" ::: "memory")
+#else
+#define BMPC_CBAR()
+#endif
+
+struct SV {  // strided view of one lane's slice of a lane-interleaved array
     double* p;
     BMPC_HD __forceinline__ double& operator[](int i) const { return p[(size_t)i * BMPC_LS]; }
     BMPC_HD __forceinline__ SV operator+(int o) const { return SV{p + (size_t)o * BMPC_LS}; }
-    // streaming read: data that will not be touched again before it is evicted anyway (the stored factor in the solves)
-    BMPC_HD __forceinline__ void sts(int i, double v) const {
-#ifdef __CUDA_ARCH__
-        __stcs(p + (size_t)i * BMPC_LS, v);
-#else
-        p[(size_t)i * BMPC_LS] = v;
-#endif
-    }
-    BMPC_HD __forceinline__ double lds(int i) const {
-#ifdef __CUDA_ARCH__
-        return __ldcs(p + (size_t)i * BMPC_LS);
-#else
-        return p[(size_t)i * BMPC_LS];
-#endif
-    }
 };
 
-template <int HZ, int NF, int LB>
-struct LaneL {
-    static constexpr int NU = NF * LB, S = HZ * NF, N = NU * HZ, MBM = 12, M = S * MBM, E = LB * LB;
-    static constexpr int o_u = 0, o_du = o_u + N, o_x = o_du + N, o_up = o_x + N, o_rd = o_up + N, o_pp = o_rd + N,
-                         o_tv = o_pp + N, o_hd = o_tv + N;
-    static constexpr int o_rs = o_hd + N, o_rl = o_rs + M, o_rdw = o_rl + M, o_rp = o_rdw + M, o_rc = o_rp + M,
-                         o_rw = o_rc + M;
-    static constexpr int o_P = o_rw + M;                 // 12 x 12 cost-to-go
-    static constexpr int o_PB = o_P + 144;               // 12 x NU
-    static constexpr int o_F = o_PB + 12 * NU;           // NU x 12
-    static constexpr int o_G = o_F + 12 * NU;            // NU x NU
-    static constexpr int o_K = o_G + NU * NU;            // per stage NU x 12 feedback gains
-    static constexpr int o_Lc = o_K + HZ * NU * 12;      // per stage Cholesky factor of G (reciprocal diagonal)
-    static constexpr int o_Rt = o_Lc + HZ * NU * NU;     // per stage input weights
-    static constexpr int o_Bm = o_Rt + HZ * NU * NU;     // per stage 6 x NU input maps in use (B, or B N in the polish)
-    static constexpr int o_B0 = o_Bm + HZ * 6 * NU;      // per stage 6 x NU input maps of the problem
-    static constexpr int o_c = o_B0 + HZ * 6 * NU;       // per stage affine term (omega, v rows)
-    static constexpr int o_rinv = o_c + HZ * 6;
-    static constexpr int o_xref = o_rinv + HZ * 9;
-    static constexpr int o_E = o_xref + HZ * 12;         // Q (X_i - xref_i)
-    static constexpr int o_Nn = o_E + HZ * 12;           // polish: null-space blocks
-    static constexpr int total = o_Nn + S * E;
+// 1/x for the barrier weights: hardware seed + two Newton steps (no special-case branch; x is a positive normal number)
+BMPC_HD __forceinline__ double rcp_nr(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// candidate inequality rows of one block in storage order (the presolve's order, bmpc_presolve.h): lower bounds of the five
+// free components, upper bounds, the four friction rows (MPC.py:220-229), the two line-foot rows (MPC.py:253-271).
+// Bit i of DevParams-derived `rowmask` says whether candidate i survived the presolve.
+template <int C> struct RLo {};
+template <int C> struct RHi {};
+template <int R> struct RFr {};
+template <int A> struct RLn {};
+
+template <int HZ, int NF>
+struct LaneRec {  // per-block record, in doubles
+    static constexpr int LB = 5, S = HZ * NF, NR = 16;
+    static constexpr int o_B3 = 0;            // 3 x 5: omega rows of the input map (dt Iw^-1 [skew(r) | I] columns of the free components)
+    static constexpr int o_ri = 15;           // 6: cz/cy, sz/cy, sz, cz, cz sy/cy, sz sy/cy of the stage (first block of a stage)
+    static constexpr int o_c = 21;            // 3: affine term of the omega rows (pinned component)
+    static constexpr int o_u = 24;            // 5: iterate / polished solution
+    static constexpr int o_xv = 29;           // 5: predictor step (polish: reduced right-hand side / solution)
+    static constexpr int o_l = 34;            // 16: multipliers
+    static constexpr int o_du = 50;           // 5: corrector / total step
+    static constexpr int o_rd = 55;           // 5: stationarity residual
+    static constexpr int o_s = 60;            // 16: slacks
+    static constexpr int o_Nn = o_du;         // 25: polish: null-space basis (aliases du, rd, s: dead by then)
+    static constexpr int o_Y = 76;            // 5 x 12: inv(L) F   (interior point: stored as float, see FT below)
+    static constexpr int o_E = o_Y;           // 12: Q (X - xref) between the two halves of a gradient evaluation (aliases Y: no factor is live then)
+    static constexpr int o_Lc = 136;          // 15: Cholesky factor of the stage's G, reciprocal diagonal
+    static constexpr int hot = 152;           // what the interior-point sweeps touch: [0, hot)
+    static constexpr int o_tv = 152;          // 5: gradient scratch (polish), diag(Hc)
+    static constexpr int o_pp = 157;          // 5: polish: particular solution of the active rows
+    static constexpr int o_am = 162;          // active-row mask of the block (polish)
+    static constexpr int o_dim = 163;         // null-space dimension of the block (polish)
+    static constexpr int REC = 164;
+    static constexpr int total = S * REC;
+    static constexpr int smem_doubles = 78;   // per lane: packed cost-to-go
 };
 
-template <int HZ, int NF, int LB>
+// F32: the interior point stores its stage factors (Y, L) as float (the Riccati recursion itself, the cost-to-go and the
+// Cholesky stay in double; the stored factor is only used by the two solves of the iteration it belongs to, whose
+// direction error ~1e-7 relative an interior point tolerates).  The polish always stores double.
+// RM: the surviving candidate rows as a compile-time mask (0 = read the mask from the parameters at run time).  With the
+// row set known to the compiler a block's rows are straight-line code in one basic block: the loads and the reciprocal
+// chains of different rows overlap.  The two row sets of the reference's limit structure are instantiated:
+constexpr unsigned kRowsRef = 0xCF9Bu;  // f_min = 0 (MPC.py:46): fx, fy, my, mz >= lo; fz, my, mz <= hi; two friction rows; line foot
+constexpr unsigned kRowsSym = 0xFF98u;  // f_min = -f_max (closed-loop workload): my, mz >= lo; fz, my, mz <= hi; four friction rows; line foot
+template <int HZ, int NF, bool F32 = true, unsigned RM = 0u>
 struct LaneSolver {
-    using L = LaneL<HZ, NF, LB>;
-    static_assert(LB == 5, "the input-map / weight layouts below are the block layouts of the register-blocked LB = 5 sweep");
-    static constexpr int NU = L::NU, S = L::S, N = L::N, E = L::E;
+    using L = LaneRec<HZ, NF>;
+    static constexpr int LB = 5, S = L::S, NR = L::NR;
     const DevParams& p;
-    SV ws;
-    double x_fb[12];
-    double Cb[L::MBM * LB], rb[L::MBM], Rd[2][LB];
-    int fo[S];  // foot of every block (stage-major)
-    // Gondzio's centrality corrector is a per-robot branch: in a warp of 32 robots some lane takes it in nearly every
-    // iteration and the other lanes idle through its extra solve.  Measured (262,144 robots, walking class): always 110.9 ms,
-    // step < 0.95 (the warp-per-robot setting) 107.5 ms, never 95.9 ms (9.5 instead of 8.6 iterations, each cheaper).
-    static constexpr bool kGondzio = false;
-    int mb, m;
-    double dt;
+    SV ws;  // global workspace slice of this lane
+    SV Ps;  // packed cost-to-go (shared memory on the device)
+    int lane_id;
+    const double* xfb;  // this robot's feedback state (re-read where it is needed instead of living in 24 registers)
+    double ln[2][LB], lnb[2];  // the two line-foot rows in block coordinates and their right-hand sides
+    unsigned footbits, rowmask;
+    double dt, vm;
 
-    BMPC_HD LaneSolver(const DevParams& pp, SV w) : p(pp), ws(w) {}
+    BMPC_HD LaneSolver(const DevParams& pp, SV w, SV ps, int lane) : p(pp), ws(w), Ps(ps), lane_id(lane) {}
+
+    // Bulk prefetch into L2 of the first `ndoubles` entries of block record v of this warp's 32 robots (one contiguous
+    // ndoubles x 256-byte panel): issued one stage ahead, so that the sweeps find their operands in L2 instead of paying the
+    // DRAM latency on every first touch (the working set of the resident warps is several times the L2).
+    BMPC_HD __forceinline__ void prefetch_rec(int v, int ndoubles) const {
+#ifdef __CUDA_ARCH__
+        if (p.lane_prefetch && v >= 0 && v < S && lane_id == __ffs(__activemask()) - 1) {
+            const double* a = ws.p - lane_id + (size_t)v * L::REC * 32;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(ndoubles * 256) : "memory");
+        }
+#endif
+    }
+    static constexpr int kFacDoubles = F32 ? 38 : 75;  // extent of the stored stage factor, in doubles
+
+    // stage factor storage: element i of [Y (60) | L (15)] of record r
+    template <bool F> BMPC_HD __forceinline__ void st_fac(SV r, int i, double x) const {
+        if constexpr (F) (reinterpret_cast<float*>(r.p + (size_t)L::o_Y * BMPC_LS) - lane_id)[(size_t)i * BMPC_LS] = (float)x;
+        else r[L::o_Y + i] = x;
+    }
+    template <bool F> BMPC_HD __forceinline__ double ld_fac(SV r, int i) const {
+        if constexpr (F) return (double)(reinterpret_cast<const float*>(r.p + (size_t)L::o_Y * BMPC_LS) - lane_id)[(size_t)i * BMPC_LS];
+        else return r[L::o_Y + i];
+    }
+
+    static BMPC_HD __forceinline__ constexpr int pk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+    static BMPC_HD __forceinline__ constexpr int tri(int a, int b) { return a * (a + 1) / 2 + b; }  // a >= b
+    static BMPC_HD __forceinline__ constexpr int comp_of(int c) { return c < 3 ? c : c + 1; }
+    BMPC_HD __forceinline__ SV rec(int v) const { return ws + v * L::REC; }
+    BMPC_HD __forceinline__ int foot_of(int v) const { return NF == 2 ? (v & 1) : (int)((footbits >> v) & 1u); }
+    BMPC_HD __forceinline__ bool dyn_of(int v) const { return NF == 1 || (v & 1) == 0; }
+    BMPC_HD __forceinline__ double Rw(int l, int c) const {  // input weight of free component c of foot l (MPC.py:28, 281)
+        const int i0 = (c < 3) ? c : (4 + c);
+        return l ? p.R[i0 + 3] : p.R[i0];
+    }
+
+    // ---- structural rows ------------------------------------------------------------------------------------------
+    template <int C> BMPC_HD __forceinline__ double rdot(RLo<C>, const double (&v)[LB]) const { return -v[C]; }
+    template <int C> BMPC_HD __forceinline__ double rdot(RHi<C>, const double (&v)[LB]) const { return v[C]; }
+    template <int R> BMPC_HD __forceinline__ double rdot(RFr<R>, const double (&v)[LB]) const {
+        return (R < 2 ? v[R & 1] : -v[R & 1]) - p.mu * v[2];
+    }
+    template <int A> BMPC_HD __forceinline__ double rdot(RLn<A>, const double (&v)[LB]) const {
+        return ln[A][0] * v[0] + ln[A][1] * v[1] + ln[A][2] * v[2] + ln[A][3] * v[3] + ln[A][4] * v[4];
+    }
+    template <int C> BMPC_HD __forceinline__ void radd(RLo<C>, double (&a)[LB], double w) const { a[C] -= w; }
+    template <int C> BMPC_HD __forceinline__ void radd(RHi<C>, double (&a)[LB], double w) const { a[C] += w; }
+    template <int R> BMPC_HD __forceinline__ void radd(RFr<R>, double (&a)[LB], double w) const {
+        a[R & 1] += (R < 2 ? w : -w);
+        a[2] -= p.mu * w;
+    }
+    template <int A> BMPC_HD __forceinline__ void radd(RLn<A>, double (&a)[LB], double w) const {
+#pragma unroll
+        for (int c = 0; c < LB; ++c) a[c] += ln[A][c] * w;
+    }
+    template <int C> BMPC_HD __forceinline__ void rrank(RLo<C>, double (&G)[15], double d) const { G[tri(C, C)] += d; }
+    template <int C> BMPC_HD __forceinline__ void rrank(RHi<C>, double (&G)[15], double d) const { G[tri(C, C)] += d; }
+    template <int R> BMPC_HD __forceinline__ void rrank(RFr<R>, double (&G)[15], double d) const {
+        const double md = p.mu * d;
+        G[tri(R & 1, R & 1)] += d;
+        G[tri(2, R & 1)] += (R < 2 ? -md : md);
+        G[tri(2, 2)] += p.mu * md;
+    }
+    template <int A> BMPC_HD __forceinline__ void rrank(RLn<A>, double (&G)[15], double d) const {
+#pragma unroll
+        for (int a = 0; a < LB; ++a) {
+            const double t = d * ln[A][a];
+#pragma unroll
+            for (int b = 0; b <= a; ++b) G[tri(a, b)] += t * ln[A][b];
+        }
+    }
+    template <int C> BMPC_HD __forceinline__ double rrhs(RLo<C>) const { return -p.lo6[comp_of(C)]; }
+    template <int C> BMPC_HD __forceinline__ double rrhs(RHi<C>) const { return p.hi6[comp_of(C)]; }
+    template <int R> BMPC_HD __forceinline__ double rrhs(RFr<R>) const { return 0.0; }
+    template <int A> BMPC_HD __forceinline__ double rrhs(RLn<A>) const { return lnb[A]; }
+    template <class T> BMPC_HD __forceinline__ void rcoef(T t, double (&c5)[LB]) const {
+#pragma unroll
+        for (int c = 0; c < LB; ++c) c5[c] = 0.0;
+        radd(t, c5, 1.0);
+    }
+
+    // f(tag, slot, k): slot = candidate index (compile-time storage position), k = index among the surviving rows
+    template <class F> BMPC_HD __forceinline__ void for_rows(F&& f) const {
+        int k = 0;
+#define BMPC_ROW(bit, tag)      \
+    if (RM ? ((RM >> (bit)) & 1u) != 0u : ((rowmask >> (bit)) & 1u) != 0u) {    \
+        f(tag{}, (bit), k);     \
+        ++k;                    \
+    }
+        BMPC_ROW(0, RLo<0>) BMPC_ROW(1, RLo<1>) BMPC_ROW(2, RLo<2>) BMPC_ROW(3, RLo<3>) BMPC_ROW(4, RLo<4>)
+        BMPC_ROW(5, RHi<0>) BMPC_ROW(6, RHi<1>) BMPC_ROW(7, RHi<2>) BMPC_ROW(8, RHi<3>) BMPC_ROW(9, RHi<4>)
+        BMPC_ROW(10, RFr<0>) BMPC_ROW(11, RFr<1>) BMPC_ROW(12, RFr<2>) BMPC_ROW(13, RFr<3>)
+        BMPC_ROW(14, RLn<0>) BMPC_ROW(15, RLn<1>)
+#undef BMPC_ROW
+    }
+
+    // everything the sweeps recompute about one row from the stored iterate and steps
+    struct RowStep {
+        double is, d, rp, dsa, dla, wc;
+    };
+    static BMPC_HD __forceinline__ RowStep row_affine(double cu, double cx, double s, double lm, double b) {
+        RowStep r;
+        r.is = rcp_nr(s);
+        r.d = lm * r.is;
+        r.rp = cu + s - b;
+        r.dsa = -r.rp - cx;
+        r.dla = -lm - r.d * r.dsa;
+        r.wc = 0.0;
+        return r;
+    }
+    // -dv / v in FP32: only a step LENGTH, cut by step_frac afterwards; NaN/Inf propagate
+    static BMPC_HD __forceinline__ float sratio(double dv, double v) { return -(float)dv / (float)v; }
+
+    // ---- structural input map: column c of B_v is [B3[0..2][c]; vm e_c (c < 3)] on the (omega, v) rows ----------------
+    BMPC_HD __forceinline__ void load_B3(SV r, double (&B3)[3][LB]) const {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < LB; ++c) B3[k][c] = r[L::o_B3 + k * LB + c];
+    }
+    // out[c] = sum_k B[k][c] x6[k]   (B' x, x on the omega/v rows)
+    BMPC_HD __forceinline__ void Bt_mul(const double (&B3)[3][LB], const double* x6, double (&out)[LB]) const {
+#pragma unroll
+        for (int c = 0; c < LB; ++c) {
+            double a = B3[0][c] * x6[0] + B3[1][c] * x6[1] + B3[2][c] * x6[2];
+            if (c < 3) a += vm * x6[3 + c];
+            out[c] = a;
+        }
+    }
+    // x6 += B u
+    BMPC_HD __forceinline__ void B_mul_add(const double (&B3)[3][LB], const double (&u)[LB], double* x6) const {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double a = x6[k];
+#pragma unroll
+            for (int c = 0; c < LB; ++c) a += B3[k][c] * u[c];
+            x6[k] = a;
+            x6[3 + k] += vm * u[k];
+        }
+    }
+    // rinv9 = dte * [[r0 r1 0] [-sz cz 0] [r6 r7 1]]  (closed form of the inverse at MPC.py:160-164)
+    BMPC_HD __forceinline__ void load_r9(SV r, double dte, double (&r9)[9]) const {
+        if (NF == 1 || dte != 0.0) {  // (the second block of a stage has A = I and no stored Rinv)
+            r9[0] = dte * r[L::o_ri + 0], r9[1] = dte * r[L::o_ri + 1], r9[2] = 0.0;
+            r9[3] = -dte * r[L::o_ri + 2], r9[4] = dte * r[L::o_ri + 3], r9[5] = 0.0;
+            r9[6] = dte * r[L::o_ri + 4], r9[7] = dte * r[L::o_ri + 5], r9[8] = dte;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 9; ++a) r9[a] = 0.0;
+        }
+    }
+    // z <- A z  (positions += D velocities),  pv <- A' pv  (velocities += D' positions); r9 already carries dt
+    static BMPC_HD __forceinline__ void A_mul(const double (&r9)[9], double dte, double (&z)[12]) {
+        z[0] += r9[0] * z[6] + r9[1] * z[7];
+        z[1] += r9[3] * z[6] + r9[4] * z[7];
+        z[2] += r9[6] * z[6] + r9[7] * z[7] + r9[8] * z[8];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) z[3 + a] += dte * z[9 + a];
+    }
+    static BMPC_HD __forceinline__ void At_mul(const double (&r9)[9], double dte, double (&pv)[12]) {
+        pv[6] += r9[0] * pv[0] + r9[3] * pv[1] + r9[6] * pv[2];
+        pv[7] += r9[1] * pv[0] + r9[4] * pv[1] + r9[7] * pv[2];
+        pv[8] += r9[8] * pv[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pv[9 + a] += dte * pv[3 + a];
+    }
+    // state reference of stage k (MPC.py:61-70), recomputed where it is needed
+    BMPC_HD __forceinline__ double xref(int k, int i) const {
+        if (k == 0) return xfb[i];
+        if (i < 6 && p.x_cmd[i + 6] != 0.0) return xfb[i] + p.x_cmd[i + 6] * (k * dt);
+        return p.x_cmd[i];
+    }
 
     // ---- objective gradient  Hc u + g  by a rollout and an adjoint sweep; optionally writes the states -------------
-    BMPC_HD void grad(SV u, SV out, double* states) {
+    // u at record offset ou, result at offset oo
+    BMPC_HD __forceinline__ void grad(int ou, int oo, double* states) {
+        BMPC_ASSUME_SPACES();
         double z[12];
 #pragma unroll
-        for (int a = 0; a < 12; ++a) z[a] = x_fb[a];
+        for (int a = 0; a < 12; ++a) z[a] = xfb[a];
 #pragma unroll 1
         for (int i = 0; i < HZ; ++i) {
-            SV ri = ws + (L::o_rinv + 9 * i), B = ws + (L::o_B0 + 6 * NU * i), c = ws + (L::o_c + 6 * i), ui = u + NU * i;
+            SV r0 = rec(i * NF);
             double acc[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) acc[k] = c[k];
-#pragma unroll 1
-            for (int col = 0; col < NU; ++col) {
-                const double uc = ui[col];
+            for (int k = 0; k < 3; ++k) acc[k] = r0[L::o_c + k], acc[3 + k] = 0.0;
+            acc[5] -= p.g * dt;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) acc[k] += B[k * NU + col] * uc;
-            }
+            for (int li = 0; li < NF; ++li) {
+                SV r = rec(i * NF + li);
+                double B3[3][LB], ui[LB];
+                load_B3(r, B3);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                z[a] += dt * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
-                z[3 + a] += dt * z[9 + a];
+                for (int c = 0; c < LB; ++c) ui[c] = r[ou + c];
+                B_mul_add(B3, ui, acc);
             }
+            double r9[9];
+            load_r9(r0, dt, r9);
+            A_mul(r9, dt, z);
 #pragma unroll
             for (int k = 0; k < 6; ++k) z[6 + k] += acc[k];
-            SV Ei = ws + (L::o_E + 12 * i), xr = ws + (L::o_xref + 12 * i);
 #pragma unroll
-            for (int a = 0; a < 12; ++a) Ei[a] = p.Q[a] * (z[a] - xr[a]);
+            for (int a = 0; a < 12; ++a) r0[L::o_E + a] = p.Q[a] * (z[a] - xref(i, a));
             if (states) {
 #pragma unroll
                 for (int a = 0; a < 12; ++a) states[13 * i + a] = z[a];
@@ -127,66 +345,29 @@ struct LaneSolver {
         for (int a = 0; a < 12; ++a) lam[a] = 0.0;
 #pragma unroll 1
         for (int i = HZ - 1; i >= 0; --i) {
-            SV ri = ws + (L::o_rinv + 9 * i), B = ws + (L::o_B0 + 6 * NU * i), Ei = ws + (L::o_E + 12 * i), ui = u + NU * i,
-               oi = out + NU * i;
+            SV r0 = rec(i * NF);
 #pragma unroll
-            for (int a = 0; a < 12; ++a) lam[a] += Ei[a];
-#pragma unroll 1
-            for (int col = 0; col < NU; ++col) {
-                double acc = Rd[fo[i * NF + col / LB]][col % LB] * ui[col];
+            for (int a = 0; a < 12; ++a) lam[a] += r0[L::o_E + a];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) acc += B[k * NU + col] * lam[6 + k];
-                oi[col] = acc;
+            for (int li = 0; li < NF; ++li) {
+                SV r = rec(i * NF + li);
+                const int l = foot_of(i * NF + li);
+                double B3[3][LB], g5[LB];
+                load_B3(r, B3);
+                Bt_mul(B3, lam + 6, g5);
+#pragma unroll
+                for (int c = 0; c < LB; ++c) r[oo + c] = Rw(l, c) * r[ou + c] + g5[c];
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                lam[6 + k] += dt * (ri[k] * lam[0] + ri[3 + k] * lam[1] + ri[6 + k] * lam[2]);
-                lam[9 + k] += dt * lam[3 + k];
-            }
+            double r9[9];
+            load_r9(r0, dt, r9);
+            At_mul(r9, dt, lam);
         }
     }
-
-    // P <- A_i' P A_i  (A = I + dt E: a column operation, then a row operation)
-    BMPC_HD void congruence(SV P, SV ri) {
-        double r9[9];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
-#pragma unroll 1
-        for (int r = 0; r < 12; ++r) {
-            const double p0 = P[r * 12], p1 = P[r * 12 + 1], p2 = P[r * 12 + 2];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                P[r * 12 + 6 + k] += p0 * r9[k] + p1 * r9[3 + k] + p2 * r9[6 + k];
-                P[r * 12 + 9 + k] += dt * P[r * 12 + 3 + k];
-            }
-        }
-#pragma unroll 1
-        for (int c = 0; c < 12; ++c) {
-            const double p0 = P[c], p1 = P[12 + c], p2 = P[24 + c];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                P[(6 + k) * 12 + c] += p0 * r9[k] + p1 * r9[3 + k] + p2 * r9[6 + k];
-                P[(9 + k) * 12 + c] += dt * P[(3 + k) * 12 + c];
-            }
-        }
-    }
-
-    // ---- backward Riccati sweep (factors  blockdiag(Rt) + B' (state cost) B  in stage-wise form) and the solves with it ----
-    BMPC_HD __forceinline__ bool factor() { return factor1(); }
-    BMPC_HD __forceinline__ void solve(SV x) { solve1(x); }
-
-    // ---- LB == 5: register-blocked sweep over VIRTUAL stages of one block (5 inputs) each; cost-to-go kept as a packed
-    //      lower triangle (78).  A stage with two stance feet is two virtual stages: Z = A X + B_0 u_0, then X' = Z + B_1 u_1 ----
-    // Per stage the only global traffic is P (read for P B, the congruence and the rank-NU update), B, Rt, and the factor
-    // pieces the solves need:  Y = inv(L) F  (NU x 12) and L  (G = L L').  K = inv(L') Y is never formed:
-    // K z = inv(L') (Y z),  K' g = Y' (inv(L) g),  F' inv(G) F = Y' Y.
-    static BMPC_HD __forceinline__ constexpr int pk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
     // P <- A' P A on the packed triangle.  A = [I D; 0 I], D = dt [Rinv 0; 0 I]:  P21 += D' P11,  P22 += D' P12new + P21old D
-    BMPC_HD void congruence_pk(SV P, SV ri) {
-        double r9[9], p11[21], n21[6][6];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) r9[a] = dt * ri[a];
+    BMPC_HD __forceinline__ void congruence_pk(const double (&r9)[9], double dte) {
+        SV P = Ps;
+        double p11[21], n21[6][6];
 #pragma unroll
         for (int e = 0; e < 21; ++e) p11[e] = P[e];
         // row by row, so that a row of the old P21 dies as soon as its row of P22 is done
@@ -197,867 +378,929 @@ struct LaneSolver {
             for (int c = 0; c < 6; ++c) {
                 o[c] = P[pk(6 + kp, c)];
                 if (kp < 3) n21[kp][c] = o[c] + r9[kp] * p11[pk(0, c)] + r9[3 + kp] * p11[pk(1, c)] + r9[6 + kp] * p11[pk(2, c)];
-                else n21[kp][c] = o[c] + dt * p11[pk(kp, c)];
+                else n21[kp][c] = o[c] + dte * p11[pk(kp, c)];
                 P[pk(6 + kp, c)] = n21[kp][c];
             }
 #pragma unroll
             for (int k = 0; k <= kp; ++k) {
                 double t1, t2;
                 if (kp < 3) t1 = r9[kp] * n21[k][0] + r9[3 + kp] * n21[k][1] + r9[6 + kp] * n21[k][2];
-                else t1 = dt * n21[k][kp];
+                else t1 = dte * n21[k][kp];
                 if (k < 3) t2 = o[0] * r9[k] + o[1] * r9[3 + k] + o[2] * r9[6 + k];
-                else t2 = dt * o[k];
+                else t2 = dte * o[k];
                 P[pk(6 + kp, 6 + k)] += t1 + t2;
             }
         }
     }
 
-    BMPC_HD __noinline__ bool factor1() {
-        static_assert(LB == 5, "register-blocked sweep is written for 5 free components per block");
-        SV P = ws + L::o_P;
-#pragma unroll 1
-        for (int e = 0; e < 78; ++e) P[e] = 0.0;
+    // t <- N' t (first `dim` components; the others 0)
+    static BMPC_HD __forceinline__ void Nt_mul(const double (&N)[LB * LB], int dim, double (&t)[LB]) {
+        double o[LB];
 #pragma unroll
-        for (int a = 0; a < 12; ++a) P[pk(a, a)] = p.Q[a];
-#pragma unroll 1
-        for (int v = S - 1; v >= 0; --v) {
-            // virtual stage v = block (stage st, foot slot li): the first block of a stage carries the dynamics A_st and the
-            // state cost of the state before it, the others act on the intermediate state (A = I, no cost)
-            const int st = v / NF;
-            const bool dyn = (v - st * NF) == 0;
-            const double dte = dyn ? dt : 0.0;
-            SV Bv = ws + (L::o_Bm + 30 * v), Rt = ws + (L::o_Rt + 25 * v), ri = ws + (L::o_rinv + 9 * st);
-            SV Y = ws + (L::o_K + 60 * v), Lc = ws + (L::o_Lc + 25 * v);
-            double B[6][5], lo[6][5], Lr[5][5];
+        for (int a = 0; a < LB; ++a) {
+            double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
+            for (int c = 0; c < LB; ++c) acc += N[c * LB + a] * t[c];
+            o[a] = (a < dim) ? acc : 0.0;
+        }
 #pragma unroll
-                for (int c = 0; c < 5; ++c) B[k][c] = Bv[k * 5 + c];
-            // rows 6..11 of P B (they also feed G); rows 0..5 are produced one at a time below so that they are never all live
+        for (int a = 0; a < LB; ++a) t[a] = o[a];
+    }
+
+    // ---- one backward stage: stage factor (Y, L stored; cost-to-go updated) + the backward half of a solve ------------
+    // G15 holds the stage's input weights on entry; rhs the block's right-hand side.  POL: inputs are w with u = N w.
+    // pv is the backward-solve vector carried from stage to stage; w (the intermediate of the solve) is stored at ow.
+    template <bool POL>
+    BMPC_HD __forceinline__ bool factor_stage(int v, SV r, double (&G)[15], const double (&rhs)[LB], double (&pv)[12], int ow,
+                                              const double (&N)[LB * LB], int dim) {
+        constexpr bool FS = F32 && !POL;
+        SV P = Ps;
+        const bool dyn = dyn_of(v);
+        const double dte = dyn ? dt : 0.0;
+        double B3[3][LB], lo[6][LB];
+        load_B3(r, B3);
+        // rows 6..11 of P B
 #pragma unroll
-            for (int r = 6; r < 12; ++r) {
-                double pr[6];
+        for (int q = 0; q < 6; ++q) {
+            double pr[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) pr[k] = P[pk(r, 6 + k)];
+            for (int k = 0; k < 6; ++k) pr[k] = P[pk(6 + q, 6 + k)];
+            Bt_mul(B3, pr, lo[q]);
+        }
+        BMPC_CBAR();
+        // G += B' (P B)[6:12]
 #pragma unroll
-                for (int c = 0; c < 5; ++c) {
+        for (int a = 0; a < LB; ++a)
+#pragma unroll
+            for (int j = 0; j <= a; ++j) {
+                double acc = G[tri(a, j)] + B3[0][a] * lo[0][j] + B3[1][a] * lo[1][j] + B3[2][a] * lo[2][j];
+                if (a < 3) acc += vm * lo[3 + a][j];
+                G[tri(a, j)] = acc;
+            }
+        if constexpr (POL) {  // G <- N' G N, identity on the padding
+            double T[LB][LB];
+#pragma unroll
+            for (int a = 0; a < LB; ++a)
+#pragma unroll
+                for (int b = 0; b < LB; ++b) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) acc += pr[k] * B[k][c];
-                    lo[r - 6][c] = acc;
-                }
-            }
-            // G = Rt + B' PB[6:12], Cholesky in registers (reciprocal diagonal)
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-#pragma unroll
-                for (int a = j; a < 5; ++a) {
-                    double v = Rt[a * 5 + j];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) v += B[k][a] * lo[k][j];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) v -= Lr[a][k] * Lr[j][k];
-                    if (a == j) {
-                        ok = ok && (v > 0.0) && (v < 1e300);
-                        Lr[j][j] = 1.0 / sqrt(v);
-                    } else {
-                        Lr[a][j] = v * Lr[j][j];
-                    }
-                }
-            }
-            if (!ok) return false;
-            // F = PB' A: row j < 6 of P B is column j of F and also adds into columns 6..11 (kept in lo); Y = inv(L) F
-            {
-                double r9[9];
-#pragma unroll
-                for (int a = 0; a < 9; ++a) r9[a] = dte * ri[a];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    double pr[6], h[5];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) pr[k] = P[pk(j, 6 + k)];
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) acc += pr[k] * B[k][c];
-                        h[c] = acc;
-                        if (j < 3) {
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) lo[k][c] += acc * r9[3 * j + k];
-                        } else {
-                            lo[j][c] += dte * acc;
-                        }
-                    }
-#pragma unroll
-                    for (int a = 0; a < 5; ++a) {
-                        double v = h[a];
-#pragma unroll
-                        for (int k = 0; k < a; ++k) v -= Lr[a][k] * h[k];
-                        h[a] = v * Lr[a][a];
-                        Y[a * 12 + j] = h[a];
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 6; ++j)
-#pragma unroll
-                for (int a = 0; a < 5; ++a) {
-                    double v = lo[j][a];
-#pragma unroll
-                    for (int k = 0; k < a; ++k) v -= Lr[a][k] * lo[j][k];
-                    lo[j][a] = v * Lr[a][a];
-                    Y[a * 12 + 6 + j] = lo[j][a];
+                    for (int c = 0; c < LB; ++c) acc += G[tri(a > c ? a : c, a > c ? c : a)] * N[c * LB + b];
+                    T[a][b] = acc;
                 }
 #pragma unroll
-            for (int a = 0; a < 5; ++a)
+            for (int a = 0; a < LB; ++a)
 #pragma unroll
-                for (int k = 0; k <= a; ++k) Lc[a * 5 + k] = Lr[a][k];
-            if (v == 0) break;
-            // P <- [Q] + A' P A - Y' Y
-            if (dyn) congruence_pk(P, ri);
-            {
-                double Yr[5][12];
+                for (int b = 0; b <= a; ++b) {
+                    double acc = 0.0;
 #pragma unroll
-                for (int a = 0; a < 5; ++a)
+                    for (int c = 0; c < LB; ++c) acc += N[c * LB + a] * T[c][b];
+                    G[tri(a, b)] = (a < dim) ? acc : ((a == b) ? 1.0 : 0.0);
+                }
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) Yr[a][j] = Y[a * 12 + j];
+            for (int q = 0; q < 6; ++q) Nt_mul(N, dim, lo[q]);
+        }
+        // Cholesky in registers (reciprocal diagonal)
+        double Lr[LB][LB];
+        bool ok = true;
 #pragma unroll
-                for (int r = 0; r < 12; ++r)
+        for (int j = 0; j < LB; ++j)
 #pragma unroll
-                    for (int c = 0; c <= r; ++c) {
-                        double acc = P[pk(r, c)];
+            for (int a = j; a < LB; ++a) {
+                double x = G[tri(a, j)];
 #pragma unroll
-                        for (int a = 0; a < 5; ++a) acc -= Yr[a][r] * Yr[a][c];
-                        if (r == c && dyn) acc += p.Q[r];
-                        P[pk(r, c)] = acc;
-                    }
+                for (int k = 0; k < j; ++k) x -= Lr[a][k] * Lr[j][k];
+                if (a == j) {
+                    ok = ok && (x > 0.0) && (x < 1e300);
+                    Lr[j][j] = 1.0 / sqrt(x);
+                } else {
+                    Lr[a][j] = x * Lr[j][j];
+                }
             }
+        if (!ok) return false;
+#pragma unroll
+        for (int a = 0; a < LB; ++a)
+#pragma unroll
+            for (int k = 0; k <= a; ++k) st_fac<FS>(r, 60 + tri(a, k), Lr[a][k]);
+        // backward half of the solve: w = inv(L) (B' pv - rhs)
+        double w[LB];
+        {
+            double g5[LB];
+            Bt_mul(B3, pv + 6, g5);
+            if constexpr (POL) Nt_mul(N, dim, g5);
+#pragma unroll
+            for (int c = 0; c < LB; ++c) {
+                double g = g5[c] - rhs[c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) g -= Lr[c][k] * w[k];
+                w[c] = g * Lr[c][c];
+                r[ow + c] = w[c];
+            }
+        }
+        // Yt = inv(L) (P B)' (before A): low half in place, P22 -= Yl' Yl
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+            for (int a = 0; a < LB; ++a) {
+                double x = lo[q][a];
+#pragma unroll
+                for (int k = 0; k < a; ++k) x -= Lr[a][k] * lo[q][k];
+                lo[q][a] = x * Lr[a][a];
+            }
+        const bool last = (v == 0);
+        if (!last) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+#pragma unroll
+                for (int k = 0; k <= q; ++k) {
+                    double acc = P[pk(6 + q, 6 + k)];
+#pragma unroll
+                    for (int a = 0; a < LB; ++a) acc -= lo[q][a] * lo[k][a];
+                    P[pk(6 + q, 6 + k)] = acc;
+                }
+        }
+        BMPC_CBAR();
+        // high half, one state column at a time: row j of P B -> column j of Yt; P21, P11 downdates; Y = Yt A
+        double hi[6][LB];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double pr[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) pr[k] = P[pk(6 + k, j)];
+            Bt_mul(B3, pr, hi[j]);
+            if constexpr (POL) Nt_mul(N, dim, hi[j]);
+#pragma unroll
+            for (int a = 0; a < LB; ++a) {
+                double x = hi[j][a];
+#pragma unroll
+                for (int k = 0; k < a; ++k) x -= Lr[a][k] * hi[j][k];
+                hi[j][a] = x * Lr[a][a];
+            }
+            if (!last) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    double acc = P[pk(6 + k, j)];
+#pragma unroll
+                    for (int a = 0; a < LB; ++a) acc -= lo[k][a] * hi[j][a];
+                    P[pk(6 + k, j)] = acc;
+                }
+#pragma unroll
+                for (int k = 0; k <= j; ++k) {
+                    double acc = P[pk(j, k)];
+#pragma unroll
+                    for (int a = 0; a < LB; ++a) acc -= hi[j][a] * hi[k][a];
+                    P[pk(j, k)] = acc;
+                }
+            }
+            BMPC_CBAR();
+        }
+        // Y = Yt A: columns 6..11 += columns 0..5 times D; store; pv <- A' pv - Y' w
+        double r9[9];
+        load_r9(r, dte, r9);
+#pragma unroll
+        for (int a = 0; a < LB; ++a) {
+            lo[0][a] += hi[0][a] * r9[0] + hi[1][a] * r9[3] + hi[2][a] * r9[6];
+            lo[1][a] += hi[0][a] * r9[1] + hi[1][a] * r9[4] + hi[2][a] * r9[7];
+            lo[2][a] += hi[2][a] * r9[8];
+#pragma unroll
+            for (int k = 3; k < 6; ++k) lo[k][a] += dte * hi[k][a];
+        }
+        At_mul(r9, dte, pv);
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+            for (int a = 0; a < LB; ++a) {
+                st_fac<FS>(r, a * 12 + j, hi[j][a]);
+                st_fac<FS>(r, a * 12 + 6 + j, lo[j][a]);
+                pv[j] -= hi[j][a] * w[a];
+                pv[6 + j] -= lo[j][a] * w[a];
+            }
+        if (last) return true;
+        BMPC_CBAR();
+        // cost-to-go of the previous state: A' P A (+ Q)
+        if (dyn) {
+            congruence_pk(r9, dte);
+#pragma unroll
+            for (int a = 0; a < 12; ++a) P[pk(a, a)] += p.Q[a];
         }
         return true;
     }
 
-    BMPC_HD __noinline__ void solve1(SV x) {
-        double pv[12];
-#pragma unroll
-        for (int a = 0; a < 12; ++a) pv[a] = 0.0;
+    BMPC_HD __forceinline__ void init_P() {
+        SV P = Ps;
 #pragma unroll 1
-        for (int v = S - 1; v >= 0; --v) {
-            const int st = v / NF;
-            const double dte = ((v - st * NF) == 0) ? dt : 0.0;
-            SV Bv = ws + (L::o_Bm + 30 * v), ri = ws + (L::o_rinv + 9 * st), Y = ws + (L::o_K + 60 * v), Lc = ws + (L::o_Lc + 25 * v),
-               xi = x + 5 * v;
-            double w[5];
+        for (int e = 0; e < 78; ++e) P[e] = 0.0;
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                double g = -xi[c];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) g += Bv[k * 5 + c] * pv[6 + k];
-#pragma unroll
-                for (int k = 0; k < c; ++k) g -= Lc[c * 5 + k] * w[k];
-                w[c] = g * Lc[c * 5 + c];
-                xi[c] = w[c];
-            }
-            double np[12];
-#pragma unroll
-            for (int a = 0; a < 12; ++a) np[a] = pv[a];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                np[6 + k] += dte * (ri[k] * pv[0] + ri[3 + k] * pv[1] + ri[6 + k] * pv[2]);
-                np[9 + k] += dte * pv[3 + k];
-            }
-#pragma unroll
-            for (int a = 0; a < 5; ++a)
-#pragma unroll
-                for (int j = 0; j < 12; ++j) np[j] -= Y.lds(a * 12 + j) * w[a];
-#pragma unroll
-            for (int a = 0; a < 12; ++a) pv[a] = np[a];
-        }
-        double z[12];
-#pragma unroll
-        for (int a = 0; a < 12; ++a) z[a] = 0.0;
-#pragma unroll 1
-        for (int v = 0; v < S; ++v) {
-            const int st = v / NF;
-            const double dte = ((v - st * NF) == 0) ? dt : 0.0;
-            SV Bv = ws + (L::o_Bm + 30 * v), ri = ws + (L::o_rinv + 9 * st), Y = ws + (L::o_K + 60 * v), Lc = ws + (L::o_Lc + 25 * v),
-               xi = x + 5 * v;
-            double t[5], xs[5];
-#pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                double v = xi[a];
-#pragma unroll
-                for (int j = 0; j < 12; ++j) v += Y.lds(a * 12 + j) * z[j];
-                t[a] = v;
-            }
-#pragma unroll
-            for (int a = 4; a >= 0; --a) {
-                double v = t[a];
-#pragma unroll
-                for (int k = a + 1; k < 5; ++k) v -= Lc[k * 5 + a] * xs[k];
-                xs[a] = v * Lc[a * 5 + a];
-            }
-            double acc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                xs[a] = -xs[a];
-                xi[a] = xs[a];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) acc[k] += Bv[k * 5 + a] * xs[a];
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                z[a] += dte * (ri[3 * a] * z[6] + ri[3 * a + 1] * z[7] + ri[3 * a + 2] * z[8]);
-                z[3 + a] += dte * z[9 + a];
-            }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) z[6 + k] += acc[k];
-        }
+        for (int a = 0; a < 12; ++a) P[pk(a, a)] = p.Q[a];
     }
 
-    // -dv / v in FP32: only a step LENGTH, cut by step_frac afterwards (same as the warp-per-robot kernel); NaN/Inf propagate
-    static BMPC_HD __forceinline__ float sratio(double dv, double v) { return -(float)dv / (float)v; }
-    BMPC_HD __forceinline__ void crow(int k, double (&cb)[LB]) const {
+    // backward half of a solve with the stored factor (one stage): w = inv(L)(B' pv - rhs) stored at ow; pv <- A' pv - Y' w
+    template <bool POL>
+    BMPC_HD __forceinline__ void solve_back_stage(int v, SV r, const double (&rhs)[LB], double (&pv)[12], int ow,
+                                                  const double (&N)[LB * LB], int dim) {
+        constexpr bool FS = F32 && !POL;
+        const double dte = dyn_of(v) ? dt : 0.0;
+        double B3[3][LB], g5[LB], w[LB], Lc[15];
+        load_B3(r, B3);
 #pragma unroll
-        for (int c = 0; c < LB; ++c) cb[c] = Cb[k * LB + c];
-    }
-    BMPC_HD __forceinline__ double cdotr(int k, const double (&v)[LB]) const {
-        double acc = 0.0;
+        for (int e = 0; e < 15; ++e) Lc[e] = ld_fac<FS>(r, 60 + e);
+        Bt_mul(B3, pv + 6, g5);
+        if constexpr (POL) Nt_mul(N, dim, g5);
 #pragma unroll
-        for (int c = 0; c < LB; ++c) acc += Cb[k * LB + c] * v[c];
-        return acc;
-    }
-    BMPC_HD __forceinline__ double cdot(int k, SV v) const {
-        double acc = 0.0;
+        for (int c = 0; c < LB; ++c) {
+            double g = g5[c] - rhs[c];
 #pragma unroll
-        for (int c = 0; c < LB; ++c) acc += Cb[k * LB + c] * v[c];
-        return acc;
-    }
-    // out_i = sign * (base_i) + (C' w)_i
-    BMPC_HD void gather(SV w, SV base, double bscale, SV out) {
-#pragma unroll 1
-        for (int j = 0; j < S; ++j) {
-            double acc[LB];
-#pragma unroll
-            for (int c = 0; c < LB; ++c) acc[c] = 0.0;
-#pragma unroll 1
-            for (int k = 0; k < mb; ++k) {
-                const double wk = w[j * mb + k];
-                double cb[LB];
-                crow(k, cb);
-#pragma unroll
-                for (int c = 0; c < LB; ++c) acc[c] += cb[c] * wk;
-            }
-#pragma unroll
-            for (int c = 0; c < LB; ++c) out[j * LB + c] = (bscale != 0.0 ? bscale * base[j * LB + c] : 0.0) + acc[c];
+            for (int k = 0; k < c; ++k) g -= Lc[tri(c, k)] * w[k];
+            w[c] = g * Lc[tri(c, c)];
+            r[ow + c] = w[c];
         }
+        double r9[9];
+        load_r9(r, dte, r9);
+        At_mul(r9, dte, pv);
+#pragma unroll
+        for (int a = 0; a < LB; ++a)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) pv[j] -= ld_fac<FS>(r, a * 12 + j) * w[a];
     }
 
-    // ---- the whole tick -------------------------------------------------------------------------------------------
+    // forward half of a solve (one stage): x = -inv(L') (w + Y z); z <- A z + B x (POL: B N x).  Returns x.
+    template <bool POL>
+    BMPC_HD __forceinline__ void solve_fwd_stage(int v, SV r, int ow, double (&z)[12], double (&xs)[LB]) const {
+        constexpr bool FS = F32 && !POL;
+        double t[LB], Lc[15];
+#pragma unroll
+        for (int e = 0; e < 15; ++e) Lc[e] = ld_fac<FS>(r, 60 + e);
+#pragma unroll
+        for (int a = 0; a < LB; ++a) {
+            double x = r[ow + a];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) x += ld_fac<FS>(r, a * 12 + j) * z[j];
+            t[a] = x;
+        }
+#pragma unroll
+        for (int a = LB - 1; a >= 0; --a) {
+            double x = t[a];
+#pragma unroll
+            for (int k = a + 1; k < LB; ++k) x -= Lc[tri(k, a)] * xs[k];
+            xs[a] = x * Lc[tri(a, a)];
+        }
+#pragma unroll
+        for (int a = 0; a < LB; ++a) xs[a] = -xs[a];
+    }
+    BMPC_HD __forceinline__ void advance_z(int v, SV r, const double (&ustep)[LB], double (&z)[12]) const {
+        const double dte = dyn_of(v) ? dt : 0.0;
+        double B3[3][LB], r9[9];
+        load_B3(r, B3);
+        load_r9(r, dte, r9);
+        A_mul(r9, dte, z);
+        B_mul_add(B3, ustep, z + 6);
+    }
+
+    // ---- group synchronisation: the warps of a CTA can run in lockstep (p.lane_sync: 0 none, 1 per iteration / phase, 2 also per
+    //      stage of every sweep) so that they fetch the same instructions at the same time.  Every thread of the group takes
+    //      the same control path; `act`-style flags, not returns, switch a lane off. ------------------------------------
+    BMPC_HD __forceinline__ bool group_any(bool x) const {
+#ifdef __CUDA_ARCH__
+        if (p.lane_sync) return __syncthreads_or(x) != 0;
+        return __any_sync(0xffffffffu, x) != 0;
+#else
+        return x;
+#endif
+    }
+    BMPC_HD __forceinline__ void stage_sync() const {
+#ifdef __CUDA_ARCH__
+        if (p.lane_sync >= 2) __syncthreads();
+#endif
+    }
+
+    // ---- the whole tick; inst < 0: no robot for this lane (it only takes part in the group's barriers) ------------------
     BMPC_HD void run(const IoPtrs& io, int inst) {
-        mb = p.mb;
-        m = S * mb;
+        BMPC_ASSUME_SPACES();
         dt = p.dt;
-        SV uv = ws + L::o_u, duv = ws + L::o_du, xv = ws + L::o_x, upv = ws + L::o_up, rdv = ws + L::o_rd, ppv = ws + L::o_pp,
-           tvp = ws + L::o_tv, hd = ws + L::o_hd;
-        SV r_s = ws + L::o_rs, r_l = ws + L::o_rl, r_d = ws + L::o_rdw, r_p = ws + L::o_rp, r_c = ws + L::o_rc, r_w = ws + L::o_rw;
-        SV Nn = ws + L::o_Nn;
+        vm = dt / p.mass;
+        // which candidate rows survived the presolve (same order as the presolve's list)
+        rowmask = 0u;
+        for (int k = 0; k < p.mb; ++k) {
+            const int kind = p.row_kind[k], arg = p.row_arg[k];
+            rowmask |= 1u << (kind == ROW_LO ? arg : kind == ROW_HI ? 5 + arg : kind == ROW_FRIC ? 10 + arg : 14 + arg);
+        }
+        const int mb = p.mb, m = S * mb;
+        const double pin = p.lo6[3];  // value of the pinned component mx
+        bool act = inst >= 0;
+        int cont0[2] = {0, 0};
+        double gs = 1.0, rdmax = 0.0;
 
-        // ---- 0. inputs; this path takes robots with exactly NF stance feet in every stage ----
-        bool bad = mb > L::MBM;
+        if (act) {
+            // ---- 0. inputs; this path takes robots with exactly NF stance feet in every stage and mx as the pinned component ----
+            bool bad = p.LB != 5 || p.npinned != 1 || p.pinned[0] != 3 || mb > NR || (RM != 0u && rowmask != RM);
+            xfb = io.x_fb + (size_t)inst * 12;
 #pragma unroll
-        for (int a = 0; a < 12; ++a) {
-            x_fb[a] = io.x_fb[(size_t)inst * 12 + a];
-            bad = bad || !isfinite(x_fb[a]);
-        }
-        double foot[6];
+            for (int a = 0; a < 12; ++a) bad = bad || !isfinite(xfb[a]);
+            double foot[6];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            foot[a] = io.foot[(size_t)inst * 6 + a];
-            bad = bad || !isfinite(foot[a]);
-        }
-        int cont0[2];
-        int blockOf[2 * HZ];
-        {
-            int j = 0;
+            for (int a = 0; a < 6; ++a) {
+                foot[a] = io.foot[(size_t)inst * 6 + a];
+                bad = bad || !isfinite(foot[a]);
+            }
+            footbits = 0u;
 #pragma unroll 1
             for (int s = 0; s < HZ; ++s) {
-                int cnt = 0;
-                for (int l = 0; l < 2; ++l) {
-                    const int c = io.contact[(size_t)inst * 2 * HZ + 2 * s + l] ? 1 : 0;
-                    if (s == 0) cont0[l] = c;
-                    blockOf[2 * s + l] = -1;
-                    if (c) {
-                        if (cnt < NF) fo[j] = l, blockOf[2 * s + l] = j, ++j;
-                        ++cnt;
-                    }
+                const int c0 = io.contact[(size_t)inst * 2 * HZ + 2 * s] ? 1 : 0, c1 = io.contact[(size_t)inst * 2 * HZ + 2 * s + 1] ? 1 : 0;
+                if (s == 0) cont0[0] = c0, cont0[1] = c1;
+                if (c0 + c1 != NF) bad = true;
+                if (NF == 1 && c1) footbits |= 1u << s;
+            }
+            // ---- 1. references, per-stage dynamics and input maps (MPC.py:61-109, 148-185) ----
+            bool singular = false;
+            double ub[LB];
+            if (!bad) {
+                const int phase_k = io.phase_k[inst];
+                double x_fb[12], rotn[9];
+#pragma unroll
+                for (int a = 0; a < 12; ++a) x_fb[a] = xfb[a];
+                const double hh = (double)p.h;
+                const double ex = p.kv * (x_fb[3] - p.x_cmd[3]), ey = p.kv * (x_fb[4] - p.x_cmd[4]);
+                const double x1 = x_fb[3] + x_fb[9] * 1 / 2 * hh / 2 * dt + ex;
+                const double x2 = x_fb[3] + x_fb[9] * 1 / 2 * hh * dt + ex;
+                const double y1 = x_fb[4] + x_fb[10] * 1 / 2 * hh / 2 * dt + ey;
+                const double y2 = x_fb[10] + x_fb[10] * 1 / 2 * hh * dt + ey;  // MPC.py:87 starts from x_fb[10]
+                eul2rotm(x_fb, rotn);
+                double u6[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const double lo = p.lo6[c], hi = p.hi6[c];
+                    const double v0 = fmin(fmax(0.0, lo + 0.1 * (hi - lo)), hi - 0.1 * (hi - lo));
+                    u6[c] = (hi > lo) ? v0 : lo;
                 }
-                if (cnt != NF) bad = true, j = (s + 1) * NF;
-            }
-        }
-        if (bad) {  // not this path's robot (or bad input): the warp-per-robot kernels take it
-            io.status[inst] = 1;
-            io.iters[inst] = 0;
-            return;
-        }
-        const int phase_k = io.phase_k[inst];
-
-        // ---- 1. references, per-stage dynamics and input maps (MPC.py:61-109, 148-185) ----
-        double rotn[9], footv[18], ub[LB];
-        {
-            const double hh = (double)p.h;
-            const double ex = p.kv * (x_fb[3] - p.x_cmd[3]), ey = p.kv * (x_fb[4] - p.x_cmd[4]);
-            const double x1 = x_fb[3] + x_fb[9] * 1 / 2 * hh / 2 * dt + ex;
-            const double x2 = x_fb[3] + x_fb[9] * 1 / 2 * hh * dt + ex;
-            const double y1 = x_fb[4] + x_fb[10] * 1 / 2 * hh / 2 * dt + ey;
-            const double y2 = x_fb[10] + x_fb[10] * 1 / 2 * hh * dt + ey;  // MPC.py:87 starts from x_fb[10]
-            for (int c = 0; c < 6; ++c) footv[c] = foot[c];
-            footv[6] = x1, footv[7] = y1, footv[8] = 0.0, footv[9] = x1, footv[10] = y1, footv[11] = 0.0;
-            footv[12] = x2, footv[13] = y2, footv[14] = 0.0, footv[15] = x2, footv[16] = y2, footv[17] = 0.0;
-            eul2rotm(x_fb, rotn);
-            double u6[6];
-            for (int c = 0; c < 6; ++c) {
-                const double lo = p.lo6[c], hi = p.hi6[c];
-                const double v0 = fmin(fmax(0.0, lo + 0.1 * (hi - lo)), hi - 0.1 * (hi - lo));
-                u6[c] = (hi > lo) ? v0 : lo;
-            }
-            u6[2] = p.lo6[2] + p.init_fz_frac * (p.hi6[2] - p.lo6[2]);
-            for (int c = 0; c < 2; ++c) {
-                const double lo = fmax(p.lo6[c], -p.mu * u6[2]), hi = fmin(p.hi6[c], p.mu * u6[2]);
-                if (p.hi6[c] > p.lo6[c]) u6[c] = 0.5 * (lo + hi);
-            }
-            for (int c = 0; c < LB; ++c) ub[c] = u6[p.comps[c]];
-            for (int l = 0; l < 2; ++l)
-                for (int c = 0; c < LB; ++c) {
-                    const int ca = p.comps[c];
-                    Rd[l][c] = p.R[(ca < 3) ? (3 * l + ca) : (6 + 3 * l + ca - 3)];
+                u6[2] = p.lo6[2] + p.init_fz_frac * (p.hi6[2] - p.lo6[2]);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const double lo = fmax(p.lo6[c], -p.mu * u6[2]), hi = fmin(p.hi6[c], p.mu * u6[2]);
+                    if (p.hi6[c] > p.lo6[c]) u6[c] = 0.5 * (lo + hi);
                 }
-        }
-        const double vm = dt / p.mass;
-        bool singular = false;
+#pragma unroll
+                for (int c = 0; c < LB; ++c) ub[c] = u6[comp_of(c)];
+                // the two line-foot rows (MPC.py:253-271) in block coordinates; the pinned component goes to the right-hand side
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const double len = (a == 0) ? p.lh_eff : p.lt_eff;
+                    const double sg = (a == 0) ? 1.0 : -1.0;
+                    ln[a][0] = -len * rotn[2], ln[a][1] = -len * rotn[5], ln[a][2] = -len * rotn[8];
+                    ln[a][3] = sg * rotn[4], ln[a][4] = sg * rotn[7];
+                    lnb[a] = 0.0 - sg * rotn[1] * pin;
+                }
+                const int kk = phase_k % 5;
+                const bool one = (cont0[0] + cont0[1] == 1);
 #pragma unroll 1
-        for (int k = 0; k < HZ; ++k) {
-            const int kk = phase_k % 5;
-            int sel = 0;
-            if (cont0[0] + cont0[1] == 1) sel = (k < 5 - kk) ? 0 : ((k < 10 - kk) ? 1 : 2);
-            double xr[12];
+                for (int k = 0; k < HZ; ++k) {
+                    int sel = 0;
+                    if (one) sel = (k < 5 - kk) ? 0 : ((k < 10 - kk) ? 1 : 2);
+                    const double xr0 = xref(k, 0), xr1 = xref(k, 1), xr2 = xref(k, 2), xr3 = xref(k, 3), xr4 = xref(k, 4), xr5 = xref(k, 5);
+                    double sz, cz, sy, cy, sx, cx;  // dynamics read x[0] as yaw, x[1] pitch, x[2] roll (MPC.py:151-153)
+                    sincos(xr0, &sz, &cz);
+                    sincos(xr1, &sy, &cy);
+                    sincos(xr2, &sx, &cx);
+                    double rot[9];  // Rx(roll) Ry(pitch) Rz(yaw)  (extrinsic 'zyx', MPC.py:156)
+                    rot[0] = cy * cz, rot[1] = -cy * sz, rot[2] = sy;
+                    rot[3] = sx * sy * cz + cx * sz, rot[4] = -sx * sy * sz + cx * cz, rot[5] = -sx * cy;
+                    rot[6] = -cx * sy * cz + sx * sz, rot[7] = cx * sy * sz + sx * cz, rot[8] = cx * cy;
+                    double tmp[9], iw[9], ii[9];
+                    mat3_mul(p.inertia, rot, tmp);
+                    mat3_tmul(rot, tmp, iw);
+                    if (!mat3_inv(iw, ii)) singular = true;
+                    const double icp = 1.0 / cy;
+                    if (!isfinite(icp) || fabs(cy) < 1e-9) singular = true;
+                    SV r0 = rec(k * NF);
+                    r0[L::o_ri + 0] = cz * icp, r0[L::o_ri + 1] = sz * icp, r0[L::o_ri + 2] = sz, r0[L::o_ri + 3] = cz;
+                    r0[L::o_ri + 4] = cz * sy * icp, r0[L::o_ri + 5] = sz * sy * icp;
+                    double cw[3] = {0, 0, 0};
 #pragma unroll
-            for (int i = 0; i < 12; ++i) xr[i] = (k == 0) ? x_fb[i] : p.x_cmd[i];
-            if (k > 0) {
+                    for (int li = 0; li < NF; ++li) {
+                        const int v = k * NF + li, l = foot_of(v);
+                        SV r = rec(v);
+                        // foot reference (MPC.py:72-109): the current feet, then foothold 1, then foothold 2 (both feet at the same x, y; z = 0)
+                        const double f0 = sel == 0 ? (l ? foot[3] : foot[0]) : (sel == 1 ? x1 : x2);
+                        const double f1 = sel == 0 ? (l ? foot[4] : foot[1]) : (sel == 1 ? y1 : y2);
+                        const double f2 = sel == 0 ? (l ? foot[5] : foot[2]) : 0.0;
+                        const double q0 = f0 - xr3, q1 = f1 - xr4, q2 = f2 - xr5;
 #pragma unroll
-                for (int i = 0; i < 6; ++i)
-                    if (p.x_cmd[i + 6] != 0.0) xr[i] = x_fb[i] + p.x_cmd[i + 6] * (k * dt);
-            }
-            SV xref = ws + (L::o_xref + 12 * k);
+                        for (int a = 0; a < 3; ++a) {  // dt Iw^{-1} [skew(r) | I]  (MPC.py:174-179, 184): columns fx fy fz (mx) my mz
+                            const double i0 = ii[3 * a], i1 = ii[3 * a + 1], i2 = ii[3 * a + 2];
+                            r[L::o_B3 + a * LB + 0] = dt * (i1 * q2 - i2 * q1);
+                            r[L::o_B3 + a * LB + 1] = dt * (i2 * q0 - i0 * q2);
+                            r[L::o_B3 + a * LB + 2] = dt * (i0 * q1 - i1 * q0);
+                            r[L::o_B3 + a * LB + 3] = dt * i1;
+                            r[L::o_B3 + a * LB + 4] = dt * i2;
+                            cw[a] += dt * i0 * pin;
+                        }
+                    }
 #pragma unroll
-            for (int i = 0; i < 12; ++i) xref[i] = xr[i];
-            double sz, cz, sy, cy, sx, cx;  // dynamics read x[0] as yaw, x[1] pitch, x[2] roll (MPC.py:151-153)
-            sincos(xr[0], &sz, &cz);
-            sincos(xr[1], &sy, &cy);
-            sincos(xr[2], &sx, &cx);
-            double rot[9];  // Rx(roll) Ry(pitch) Rz(yaw)  (extrinsic 'zyx', MPC.py:156)
-            rot[0] = cy * cz, rot[1] = -cy * sz, rot[2] = sy;
-            rot[3] = sx * sy * cz + cx * sz, rot[4] = -sx * sy * sz + cx * cz, rot[5] = -sx * cy;
-            rot[6] = -cx * sy * cz + sx * sz, rot[7] = cx * sy * sz + sx * cz, rot[8] = cx * cy;
-            double tmp[9], iw[9], ii[9];
-            mat3_mul(p.inertia, rot, tmp);
-            mat3_tmul(rot, tmp, iw);
-            if (!mat3_inv(iw, ii)) singular = true;
-            const double icp = 1.0 / cy;
-            if (!isfinite(icp) || fabs(cy) < 1e-9) singular = true;
-            SV ri = ws + (L::o_rinv + 9 * k);
-            ri[0] = cz * icp, ri[1] = sz * icp, ri[2] = 0.0;
-            ri[3] = -sz, ri[4] = cz, ri[5] = 0.0;
-            ri[6] = cz * sy * icp, ri[7] = sz * sy * icp, ri[8] = 1.0;
-            double cw[6] = {0, 0, 0, 0, 0, 0};
-            SV B0 = ws + (L::o_B0 + 6 * NU * k);
-            for (int li = 0; li < NF; ++li) {
-                const int l = fo[k * NF + li];
-                const double* fr = footv + 6 * sel + 3 * l;
-                const double r0 = fr[0] - xr[3], r1 = fr[1] - xr[4], r2 = fr[2] - xr[5];
-                double B[18];  // dt Iw^{-1} [skew(r) | I]  (MPC.py:174-179, 184)
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const double i0 = ii[3 * a], i1 = ii[3 * a + 1], i2 = ii[3 * a + 2];
-                    B[6 * a + 0] = dt * (i1 * r2 - i2 * r1);
-                    B[6 * a + 1] = dt * (i2 * r0 - i0 * r2);
-                    B[6 * a + 2] = dt * (i0 * r1 - i1 * r0);
-                    B[6 * a + 3] = dt * i0, B[6 * a + 4] = dt * i1, B[6 * a + 5] = dt * i2;
+                    for (int a = 0; a < 3; ++a) r0[L::o_c + a] = cw[a];
                 }
-                for (int a = 0; a < 3; ++a) {
+            }
+            if (bad || singular) {  // not this path's robot (or bad input): the warp-per-robot kernels take it
+                io.status[inst] = 1;
+                io.iters[inst] = 0;
+                act = false;
+            }
+
+            // ---- 2. interior point: start ----
+            if (act) {
+                // g = gradient at u = 0 (scale of the problem)
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) r[L::o_u + c] = 0.0;
+                }
+                grad(L::o_u, L::o_tv, nullptr);
+                gs = 0.0;
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) gs = fmax(gs, fabs(r[L::o_tv + c]));
+                }
+                gs += 1.0;
+                // start point: the same interior point in every block
+                double part = 0.0;
+                double sl0[NR];
+                for_rows([&](auto tag, int slot, int) {
+                    double sl = rrhs(tag) - rdot(tag, ub);
+                    if (!(sl > 1e-3)) sl = 1.0;
+                    sl0[slot] = sl;
+                    part += sl * (double)S;
+                });
+                const double mu0 = p.mu0_scale * part / (double)m;
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) r[L::o_u + c] = ub[c];
+                    for_rows([&](auto, int slot, int) {
+                        r[L::o_s + slot] = sl0[slot];
+                        r[L::o_l + slot] = mu0 / sl0[slot];
+                    });
+                }
+                grad(L::o_u, L::o_tv, nullptr);
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {  // rd = Hc u + g + C' lam
+                    SV r = rec(v);
+                    double acc[LB];
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) acc[c] = r[L::o_tv + c];
+                    for_rows([&](auto tag, int slot, int) { radd(tag, acc, r[L::o_l + slot]); });
+#pragma unroll
                     for (int c = 0; c < LB; ++c) {
-                        B0[a * NU + li * LB + c] = B[6 * a + p.comps[c]];
-                        B0[(3 + a) * NU + li * LB + c] = (p.comps[c] == a) ? vm : 0.0;
-                    }
-                    for (int c = 0; c < p.npinned; ++c) {
-                        cw[a] += B[6 * a + p.pinned[c]] * p.lo6[p.pinned[c]];
-                        if (p.pinned[c] == a) cw[3 + a] += vm * p.lo6[p.pinned[c]];
+                        r[L::o_rd + c] = acc[c];
+                        rdmax = fmax(rdmax, fabs(acc[c]));
                     }
                 }
             }
-            cw[5] -= p.g * dt;
-            SV cc = ws + (L::o_c + 6 * k);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) cc[a] = cw[a];
-        }
-        if (singular) {
-            io.status[inst] = 1;
-            io.iters[inst] = 0;
-            return;
-        }
-        // per-block inequality rows in block coordinates (MPC.py:220-271), the same for every block
-        for (int k = 0; k < mb; ++k) {
-            const int kind = p.row_kind[k], arg = p.row_arg[k];
-            double f6[6] = {0, 0, 0, 0, 0, 0};
-            double rhs = 0.0;
-            if (kind == ROW_LO) {
-                f6[p.comps[arg]] = -1.0;
-                rhs = -p.lo6[p.comps[arg]];
-            } else if (kind == ROW_HI) {
-                f6[p.comps[arg]] = 1.0;
-                rhs = p.hi6[p.comps[arg]];
-            } else if (kind == ROW_FRIC) {
-                f6[arg & 1] = (arg < 2) ? 1.0 : -1.0;
-                f6[2] = -p.mu;
-            } else {
-                const double len = (arg == 0) ? p.lh_eff : p.lt_eff;
-                const double sg = (arg == 0) ? 1.0 : -1.0;
-                f6[0] = -len * rotn[2], f6[1] = -len * rotn[5], f6[2] = -len * rotn[8];
-                f6[3] = sg * rotn[1], f6[4] = sg * rotn[4], f6[5] = sg * rotn[7];
-            }
-            for (int c = 0; c < p.npinned; ++c) rhs -= f6[p.pinned[c]] * p.lo6[p.pinned[c]];
-            for (int c = 0; c < LB; ++c) Cb[k * LB + c] = f6[p.comps[c]];
-            rb[k] = rhs;
-        }
-
-        // ---- 2. interior point ----
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) uv[i] = 0.0;
-        grad(uv, tvp, nullptr);  // g = gradient at u = 0
-        double gs = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) gs = fmax(gs, fabs(tvp[i]));
-        gs += 1.0;
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) uv[i] = ub[i % LB];
-        double part = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < mb; ++k) {
-            double sl = rb[k];
-            for (int c = 0; c < LB; ++c) sl -= Cb[k * LB + c] * ub[c];
-            if (!(sl > 1e-3)) sl = 1.0;
-            for (int j = 0; j < S; ++j) r_s[j * mb + k] = sl;
-            part += sl * (double)S;
-        }
-        const double mu0 = p.mu0_scale * part / (double)m;
-#pragma unroll 1
-        for (int r = 0; r < m; ++r) r_l.sts(r, mu0 / r_s.lds(r));
-#pragma unroll 1
-        for (int j = 0; j < S; ++j) {  // input maps in use, block layout [block][6][LB] (the problem's maps B0 are [stage][6][NU])
-            const int st = j / NF, li = j - st * NF;
-            for (int k = 0; k < 6; ++k)
-                for (int c = 0; c < LB; ++c) ws[L::o_Bm + (j * 6 + k) * LB + c] = ws[L::o_B0 + 6 * NU * st + k * NU + li * LB + c];
         }
 
         const double mu_target = p.mu_tol * gs;
         int status = 1, it = 0;
-        double mu = 0.0, rdmax = 0.0;
-        bool rd_fresh = false;
-        double alpha_prev = 0.0;
+        double alpha = 0.0, tgt = 0.0;
+        const double dummyN[LB * LB] = {0.0};  // (unused: the interior point works on the inputs themselves)
+        bool ipm = act;
 #pragma unroll 1
-        while (true) {
-            if (it >= p.max_iter) {
-                status = 1;
-                break;
-            }
-            ++it;
-            if (!rd_fresh) {
-                grad(uv, tvp, nullptr);
-                gather(r_l, tvp, 1.0, rdv);
-                rdmax = 0.0;
-#pragma unroll 1
-                for (int i = 0; i < N; ++i) rdmax = fmax(rdmax, fabs(rdv[i]));
-                rd_fresh = true;
-            }
-            // One pass per block: barrier weights d = lam / s, primal residuals, the predictor right-hand side
-            // -rd - C'(d rp - lam) and the stage input weights R + Cb' diag(d) Cb (written where the sweep reads them)
-            part = 0.0;
-#pragma unroll 1
-            for (int j = 0; j < S; ++j) {
-                double vb[LB], gacc[LB], acc[LB * (LB + 1) / 2];
+        while (group_any(ipm)) {
+            if (ipm && it >= p.max_iter) status = 1, ipm = false;
+            if (ipm) ++it;
+            // -- sweep A (backward): apply the previous step, barrier weights, right-hand side, stage factor, backward half
+            //    of the predictor solve
+            double pv[12];
+            double part = 0.0;
+            if (ipm) {
+                init_P();
 #pragma unroll
-                for (int c = 0; c < LB; ++c) {  // the previous iteration's step is applied here (alpha_prev = 0 in the first one)
-                    vb[c] = uv[j * LB + c];
-                    gacc[c] = rdv[j * LB + c];
-                    if (alpha_prev != 0.0) {  // (duv is uninitialised before the first step)
-                        vb[c] += alpha_prev * duv[j * LB + c];
-                        gacc[c] *= (1.0 - alpha_prev);
-                        uv[j * LB + c] = vb[c];
-                        rdv[j * LB + c] = gacc[c];
+                for (int a = 0; a < 12; ++a) pv[a] = 0.0;
+            }
+#pragma unroll 1
+            for (int v = S - 1; v >= 0; --v) {
+                stage_sync();
+                if (!ipm) continue;
+                prefetch_rec(v - 1, L::o_Y);
+                SV r = rec(v);
+                const int l = foot_of(v);
+                double u[LB], gacc[LB], G[15], x5[LB], d5[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) {
+                    u[c] = r[L::o_u + c];
+                    gacc[c] = r[L::o_rd + c];
+                    x5[c] = d5[c] = 0.0;
+                }
+                const bool apply = alpha != 0.0;  // (du is not initialised before the first step)
+                if (apply) {
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) {
+                        x5[c] = r[L::o_xv + c];
+                        d5[c] = r[L::o_du + c];
+                        gacc[c] *= (1.0 - alpha);
+                        r[L::o_rd + c] = gacc[c];
+                        r[L::o_u + c] = u[c] + alpha * d5[c];
                     }
                 }
 #pragma unroll
                 for (int a = 0; a < LB; ++a)
 #pragma unroll
-                    for (int b2 = 0; b2 <= a; ++b2) acc[a * (a + 1) / 2 + b2] = (a == b2) ? Rd[fo[j]][a] : 0.0;
-#pragma unroll 1
-                for (int k = 0; k < mb; ++k) {
-                    const int r = j * mb + k;
-                    double s = r_s.lds(r), l = r_l.lds(r);
-                    if (alpha_prev != 0.0) {
-                        s += alpha_prev * r_p.lds(r);
-                        l += alpha_prev * r_c.lds(r);
-                        r_s.sts(r, s);
-                        r_l.sts(r, l);
+                    for (int b = 0; b <= a; ++b) G[tri(a, b)] = (a == b) ? Rw(l, a) : 0.0;
+                for_rows([&](auto tag, int slot, int) {
+                    double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                    const double b = rrhs(tag);
+                    double cu = rdot(tag, u);
+                    if (apply) {
+                        const double cx = rdot(tag, x5), cd = rdot(tag, d5);
+                        RowStep q = row_affine(cu, cx, s, lm, b);
+                        const double wc = (q.dsa * q.dla - tgt) * q.is;
+                        const double ds = -q.rp - cd, dl = -lm - wc - q.d * ds;
+                        s += alpha * ds;
+                        lm += alpha * dl;
+                        cu += alpha * cd;
+                        r[L::o_s + slot] = s;
+                        r[L::o_l + slot] = lm;
                     }
-                    double cb[LB];
-                    crow(k, cb);
-                    double cu = 0.0;
+                    const double d = lm * rcp_nr(s), rp = cu + s - b;
+                    part += s * lm;
+                    radd(tag, gacc, d * rp - lm);
+                    rrank(tag, G, d);
+                });
+                double rhs[LB];
 #pragma unroll
-                    for (int c = 0; c < LB; ++c) cu += cb[c] * vb[c];
-                    const double d = l / s, rp = cu + s - rb[k];
-                    r_p.sts(r, rp);
-                    const double w = d * rp - l;
-                    part += s * l;
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) gacc[c] += cb[c] * w;
-#pragma unroll
-                    for (int a = 0; a < LB; ++a)
-#pragma unroll
-                        for (int b2 = 0; b2 <= a; ++b2) acc[a * (a + 1) / 2 + b2] += cb[a] * cb[b2] * d;
-                }
-#pragma unroll
-                for (int c = 0; c < LB; ++c) xv[j * LB + c] = -gacc[c];
-                SV Rt = ws + (L::o_Rt + LB * LB * j);  // block layout: the sweep reads one LB x LB block per virtual stage
-#pragma unroll
-                for (int a = 0; a < LB; ++a)
-#pragma unroll
-                    for (int b2 = 0; b2 <= a; ++b2) Rt[a * LB + b2] = acc[a * (a + 1) / 2 + b2];
+                for (int c = 0; c < LB; ++c) rhs[c] = -gacc[c];
+                if (!factor_stage<false>(v, r, G, rhs, pv, L::o_xv, dummyN, LB)) status = 2, ipm = false;
             }
-            mu = part / (double)m;
-            if (mu <= mu_target && rdmax <= p.rd_tol * mu_target) {
-                status = 0;
-                break;
-            }
-            if (!factor()) {
-                status = 2;
-                break;
-            }
-            solve(xv);
+            const double mu = part / (double)m;
+            // -- sweep B (forward): predictor step and its statistics
             float ratio = 0.f;
             part = 0.0;
-#pragma unroll 1
-            for (int j = 0; j < S; ++j) {
-                double vb[LB];
+            {
+                double z[12];
 #pragma unroll
-                for (int c = 0; c < LB; ++c) vb[c] = xv[j * LB + c];
+                for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
-                for (int k = 0; k < mb; ++k) {
-                    const int r = j * mb + k;
-                    const double sr = r_s.lds(r), lr = r_l.lds(r);
-                    const double dsa = -r_p.lds(r) - cdotr(k, vb);
-                    const double dla = -lr - (lr / sr) * dsa;
-                    ratio = fmaxf(ratio, fmaxf(sratio(dsa, sr), sratio(dla, lr)));
-                    r_c.sts(r, dsa * dla);
-                    part += dsa * dla;
+                for (int v = 0; v < S; ++v) {
+                    stage_sync();
+                    if (!ipm) continue;
+                    prefetch_rec(v + 1, L::o_Y + kFacDoubles);
+                    SV r = rec(v);
+                    double xs[LB], u[LB];
+                    solve_fwd_stage<false>(v, r, L::o_xv, z, xs);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) {
+                        r[L::o_xv + c] = xs[c];
+                        u[c] = r[L::o_u + c];
+                    }
+                    advance_z(v, r, xs, z);
+                    for_rows([&](auto tag, int slot, int) {
+                        const double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                        const RowStep q = row_affine(rdot(tag, u), rdot(tag, xs), s, lm, rrhs(tag));
+                        ratio = fmaxf(ratio, fmaxf(sratio(q.dsa, s), sratio(q.dla, lm)));
+                        part += q.dsa * q.dla;
+                    });
                 }
             }
-            const double a_aff = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
-            const double mu_aff = mu * (1.0 - a_aff) + a_aff * a_aff * part / (double)m;
-            double sigma = mu_aff / mu;
-            sigma = sigma * sigma * sigma;
-            const double tgt = sigma * mu;
-            // corrector right-hand side C' wc, wc = (dsa dla - sigma mu) / s   (solved in duv, the affine step stays in xv)
-#pragma unroll 1
-            for (int j = 0; j < S; ++j) {
-                double gacc[LB];
+            if (ipm) {
+                const double a_aff = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
+                const double mu_aff = mu * (1.0 - a_aff) + a_aff * a_aff * part / (double)m;
+                double sigma = mu_aff / mu;
+                sigma = sigma * sigma * sigma;
+                tgt = sigma * mu;
 #pragma unroll
-                for (int c = 0; c < LB; ++c) gacc[c] = 0.0;
-#pragma unroll 1
-                for (int k = 0; k < mb; ++k) {
-                    const int r = j * mb + k;
-                    const double wc = (r_c.lds(r) - tgt) / r_s.lds(r);
-                    r_c.sts(r, wc);
-                    double cb[LB];
-                    crow(k, cb);
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) gacc[c] += cb[c] * wc;
-                }
-#pragma unroll
-                for (int c = 0; c < LB; ++c) duv[j * LB + c] = gacc[c];
+                for (int a = 0; a < 12; ++a) pv[a] = 0.0;
             }
-            solve(duv);
+            // -- sweep C (backward): corrector right-hand side C' wc, wc = (dsa dla - sigma mu) / s, backward half of its solve
 #pragma unroll 1
-            for (int i = 0; i < N; ++i) duv[i] += xv[i];
+            for (int v = S - 1; v >= 0; --v) {
+                stage_sync();
+                if (!ipm) continue;
+                prefetch_rec(v - 1, L::o_Y + kFacDoubles);
+                SV r = rec(v);
+                double u[LB], x5[LB], gacc[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) {
+                    u[c] = r[L::o_u + c];
+                    x5[c] = r[L::o_xv + c];
+                    gacc[c] = 0.0;
+                }
+                for_rows([&](auto tag, int slot, int) {
+                    const double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                    const RowStep q = row_affine(rdot(tag, u), rdot(tag, x5), s, lm, rrhs(tag));
+                    radd(tag, gacc, (q.dsa * q.dla - tgt) * q.is);
+                });
+                solve_back_stage<false>(v, r, gacc, pv, L::o_du, dummyN, LB);
+            }
+            // -- sweep D (forward): total step, step length, complementarity after the step
             ratio = 0.f;
-#pragma unroll 1
-            for (int j = 0; j < S; ++j) {
-                double vb[LB];
+            double sum_sl = 0.0, sum_x = 0.0, sum_dd = 0.0;
+            {
+                double z[12];
 #pragma unroll
-                for (int c = 0; c < LB; ++c) vb[c] = duv[j * LB + c];
+                for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
-                for (int k = 0; k < mb; ++k) {
-                    const int r = j * mb + k;
-                    const double sr = r_s.lds(r), lr = r_l.lds(r);
-                    const double ds = -r_p.lds(r) - cdotr(k, vb);
-                    const double dl = -lr - r_c.lds(r) - (lr / sr) * ds;
-                    ratio = fmaxf(ratio, fmaxf(sratio(ds, sr), sratio(dl, lr)));
-                    r_p.sts(r, ds);
-                    r_c.sts(r, dl);
+                for (int v = 0; v < S; ++v) {
+                    stage_sync();
+                    if (!ipm) continue;
+                    prefetch_rec(v + 1, L::o_Y + kFacDoubles);
+                    SV r = rec(v);
+                    double xs[LB], u[LB], x5[LB], d5[LB];
+                    solve_fwd_stage<false>(v, r, L::o_du, z, xs);
+                    advance_z(v, r, xs, z);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) {
+                        u[c] = r[L::o_u + c];
+                        x5[c] = r[L::o_xv + c];
+                        d5[c] = xs[c] + x5[c];
+                        r[L::o_du + c] = d5[c];
+                    }
+                    for_rows([&](auto tag, int slot, int) {
+                        const double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                        const RowStep q = row_affine(rdot(tag, u), rdot(tag, x5), s, lm, rrhs(tag));
+                        const double wc = (q.dsa * q.dla - tgt) * q.is;
+                        const double ds = -q.rp - rdot(tag, d5), dl = -lm - wc - q.d * ds;
+                        ratio = fmaxf(ratio, fmaxf(sratio(ds, s), sratio(dl, lm)));
+                        sum_sl += s * lm;
+                        sum_x += s * dl + lm * ds;
+                        sum_dd += ds * dl;
+                    });
                 }
             }
-            double a2 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
-            if (!isfinite(ratio)) {
-                status = 2;
-                break;
-            }
-            if (kGondzio && p.gondzio && a2 < p.gondzio_below) {
-                const double at = fmin(1.0, 1.5 * a2 + 0.1);
-#pragma unroll 1
-                for (int r = 0; r < m; ++r) {
-                    const double v = (r_s.lds(r) + at * r_p.lds(r)) * (r_l.lds(r) + at * r_c.lds(r));
-                    double vt = fmin(fmax(v, 0.1 * tgt), 10.0 * tgt) - v;
-                    vt = fmax(vt, -10.0 * tgt);
-                    r_w[r] = -vt / r_s.lds(r);
-                }
-                gather(r_w, xv, 0.0, xv);
-                solve(xv);
-                ratio = 0.f;
-#pragma unroll 1
-                for (int j = 0; j < S; ++j) {
-                    double vb[LB];
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) vb[c] = xv[j * LB + c];
-#pragma unroll 1
-                    for (int k = 0; k < mb; ++k) {
-                        const int r = j * mb + k;
-                        const double cx = cdotr(k, vb);
-                        const double ds = r_p.lds(r) - cx;
-                        const double dl = r_c.lds(r) + r_d[r] * cx - r_w[r];
-                        ratio = fmaxf(ratio, fmaxf(sratio(ds, r_s.lds(r)), sratio(dl, r_l.lds(r))));
+            if (ipm) {
+                if (!isfinite(ratio)) {
+                    status = 2, ipm = false;
+                } else {
+                    const double a2 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
+                    alpha = (it > 14 ? 0.9 : p.step_frac) * a2;  // applied by the next sweep A (or by the hand-over below)
+                    rdmax *= (1.0 - alpha);
+                    const double mu_next = (sum_sl + alpha * (sum_x + alpha * sum_dd)) / (double)m;
+                    if (mu_next <= mu_target && rdmax <= p.rd_tol * mu_target) {
+                        status = 0;
+                        ++it;  // (the iteration count includes the one that only tests convergence, as in the warp-per-robot kernels)
+                        ipm = false;
                     }
                 }
-                const double a3 = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
-                if (isfinite(ratio) && a3 > a2) {
-                    a2 = a3;
-#pragma unroll 1
-                    for (int j = 0; j < S; ++j) {
-                        double vb[LB];
-#pragma unroll
-                        for (int c = 0; c < LB; ++c) vb[c] = xv[j * LB + c];
-#pragma unroll 1
-                        for (int k = 0; k < mb; ++k) {
-                            const int r = j * mb + k;
-                            const double cx = cdotr(k, vb);
-                            r_p.sts(r, r_p.lds(r) - (cx));
-                            r_c.sts(r, r_c.lds(r) + (r_d[r] * cx - r_w[r]));
-                        }
-                    }
-#pragma unroll 1
-                    for (int i = 0; i < N; ++i) duv[i] += xv[i];
-                }
             }
-            // the step (u, s, lam, rd) is applied by the next iteration's first pass
-            alpha_prev = (it > 14 ? 0.9 : p.step_frac) * a2;
-            rdmax *= (1.0 - alpha_prev);
         }
 
         // ---- 3. active-set polish + certificate (one attempt; anything else goes to the warp-per-robot kernels) ----
-        int amask[S], bdim[S];
-        bool polished = false;
-        if (status == 0) {
-            // diag(Hc) from the uncontrolled cost-to-go
-            {
-                SV P = ws + L::o_P;
+        bool pol = act && status == 0, polished = false;
+        double Cb[NR * LB], rb[NR];  // dense copy of the block rows for the per-block null-space / multiplier functions (polish only)
+        if (pol) {
+            // diag(Hc) from the uncontrolled cost-to-go (into tv)
+            init_P();
 #pragma unroll 1
-                for (int e = 0; e < 144; ++e) P[e] = 0.0;
+            for (int i = HZ - 1; i >= 0; --i) {
+                SV P = Ps;
 #pragma unroll
-                for (int a = 0; a < 12; ++a) P[a * 13] = p.Q[a];
-#pragma unroll 1
-                for (int i = HZ - 1; i >= 0; --i) {
-                    SV B = ws + (L::o_B0 + 6 * NU * i);
-#pragma unroll 1
-                    for (int c = 0; c < NU; ++c) {
-                        double b[6], acc = Rd[fo[i * NF + c / LB]][c % LB];
+                for (int li = 0; li < NF; ++li) {
+                    const int v = i * NF + li, l = foot_of(v);
+                    SV r = rec(v);
+                    double B3[3][LB];
+                    load_B3(r, B3);
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) b[k] = B[k * NU + c];
+                    for (int c = 0; c < LB; ++c) {
+                        double b6[6] = {B3[0][c], B3[1][c], B3[2][c], 0.0, 0.0, 0.0};
+                        if (c < 3) b6[3 + c] = vm;
+                        double acc = Rw(l, c);
 #pragma unroll
                         for (int k = 0; k < 6; ++k)
 #pragma unroll
-                            for (int k2 = 0; k2 < 6; ++k2) acc += b[k] * P[(6 + k) * 12 + 6 + k2] * b[k2];
-                        hd[i * NU + c] = acc;
+                            for (int k2 = 0; k2 < 6; ++k2)
+                                if ((k < 3 || k == 3 + c) && (k2 < 3 || k2 == 3 + c)) acc += b6[k] * P[pk(6 + k, 6 + k2)] * b6[k2];
+                        r[L::o_tv + c] = acc;
                     }
-                    if (i == 0) break;
-                    congruence(P, ws + (L::o_rinv + 9 * i));
-#pragma unroll
-                    for (int a = 0; a < 12; ++a) P[a * 13] += p.Q[a];
                 }
+                if (i == 0) break;
+                double r9[9];
+                load_r9(rec(i * NF), dt, r9);
+                congruence_pk(r9, dt);
+#pragma unroll
+                for (int a = 0; a < 12; ++a) P[pk(a, a)] += p.Q[a];
             }
+            // hand-over: apply the last step to (s, lam); rows whose barrier weight dominates the curvature along them are active
 #pragma unroll 1
-            for (int j = 0; j < S; ++j) {
-                int mk = 0;
-#pragma unroll 1
-                for (int k = 0; k < mb; ++k) {
+            for (int v = 0; v < S; ++v) {
+                SV r = rec(v);
+                double u[LB], x5[LB], d5[LB], hd[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) u[c] = r[L::o_u + c], x5[c] = r[L::o_xv + c], d5[c] = r[L::o_du + c], hd[c] = r[L::o_tv + c];
+                unsigned mk = 0u;
+                for_rows([&](auto tag, int slot, int k) {
+                    double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                    const RowStep q = row_affine(rdot(tag, u), rdot(tag, x5), s, lm, rrhs(tag));
+                    const double wc = (q.dsa * q.dla - tgt) * q.is;
+                    const double ds = -q.rp - rdot(tag, d5), dl = -lm - wc - q.d * ds;
+                    s += alpha * ds;
+                    lm += alpha * dl;
+                    r[L::o_l + slot] = lm;
+                    double c5[LB];
+                    rcoef(tag, c5);
                     double th = 0.0, aa = 0.0;
 #pragma unroll
-                    for (int c = 0; c < LB; ++c) th += Cb[k * LB + c] * Cb[k * LB + c] * hd[j * LB + c], aa += Cb[k * LB + c] * Cb[k * LB + c];
-                    if (r_l[j * mb + k] * fmax(aa * aa, 1e-300) > th * r_s[j * mb + k]) mk |= 1 << k;
-                }
-                amask[j] = mk;
+                    for (int c = 0; c < LB; ++c) th += c5[c] * c5[c] * hd[c], aa += c5[c] * c5[c];
+                    if (lm * fmax(aa * aa, 1e-300) > th * s) mk |= 1u << k;
+                });
+                r[L::o_am] = (double)mk;
             }
+            for_rows([&](auto tag, int, int k) {
+                double c5[LB];
+                rcoef(tag, c5);
+#pragma unroll
+                for (int c = 0; c < LB; ++c) Cb[k * LB + c] = c5[c];
+                rb[k] = rrhs(tag);
+            });
             status = 1;
+        }
+        int round = 0;
 #pragma unroll 1
-            for (int round = 0; round < p.polish_rounds; ++round) {
+        while (group_any(pol)) {
+            if (pol && round >= p.polish_rounds) pol = false;
+            ++round;
+            double pv[12];
+            if (pol) {
                 bool bad_blk = false;
 #pragma unroll 1
-                for (int j = 0; j < S; ++j) {
-                    double pl[LB], Nl[E];
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+                    double pl[LB], Nl[LB * LB];
                     int dim = 0;
-                    if (!block_nullspace<LB>(Cb, rb, mb, (unsigned)amask[j], pl, Nl, &dim)) bad_blk = true;
-                    bdim[j] = dim;
-                    for (int c = 0; c < LB; ++c) ppv[j * LB + c] = pl[c];
-                    for (int e = 0; e < E; ++e) Nn[j * E + e] = Nl[e];
+                    if (!block_nullspace<LB>(Cb, rb, mb, (unsigned)r[L::o_am], pl, Nl, &dim)) bad_blk = true;
+                    r[L::o_dim] = (double)dim;
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) r[L::o_pp + c] = pl[c];
+#pragma unroll
+                    for (int e = 0; e < LB * LB; ++e) r[L::o_Nn + e] = Nl[e];
                 }
-                if (bad_blk) break;
-                grad(ppv, tvp, nullptr);
-                // reduced LQR: inputs w_b, maps B_b N_b, weights N_b' R N_b (+ I on the padding)
-#pragma unroll 1
-                for (int s = 0; s < HZ; ++s) {
-                    SV B0 = ws + (L::o_B0 + 6 * NU * s);
-                    for (int li = 0; li < NF; ++li) {
-                        const int j = s * NF + li, dim = bdim[j];
-                        SV Nj = Nn + j * E, Rt = ws + (L::o_Rt + LB * LB * j), Bm = ws + (L::o_Bm + 6 * LB * j);  // block layouts
-#pragma unroll 1
-                        for (int a = 0; a < LB; ++a) {
-                            double acc = 0.0;
+                if (bad_blk) pol = false;
+            }
+            if (pol) {
+                grad(L::o_pp, L::o_tv, nullptr);
+                // reduced LQR: inputs w_b with u_b = p_b + N_b w_b; backward sweep (factor + backward half), then forward
+                init_P();
 #pragma unroll
-                            for (int c = 0; c < LB; ++c) acc += Nj[c * LB + a] * tvp[j * LB + c];
-                            xv[j * LB + a] = (a < dim) ? -acc : 0.0;
+                for (int a = 0; a < 12; ++a) pv[a] = 0.0;
+            }
 #pragma unroll 1
-                            for (int b = 0; b <= a; ++b) {
-                                double w = 0.0;
+            for (int v = S - 1; v >= 0; --v) {
+                stage_sync();
+                if (!pol) continue;
+                prefetch_rec(v - 1, L::REC);
+                SV r = rec(v);
+                const int l = foot_of(v);
+                double N[LB * LB], G[15], rhs[LB];
+                const int dim = (int)r[L::o_dim];
 #pragma unroll
-                                for (int c = 0; c < LB; ++c) w += Nj[c * LB + a] * Rd[fo[j]][c] * Nj[c * LB + b];
-                                if (a == b && a >= dim) w = 1.0;
-                                Rt[a * LB + b] = w;
-                            }
+                for (int e = 0; e < LB * LB; ++e) N[e] = r[L::o_Nn + e];
 #pragma unroll
-                            for (int k = 0; k < 6; ++k) {
-                                double w = 0.0;
+                for (int c = 0; c < LB; ++c) rhs[c] = -r[L::o_tv + c];
+                Nt_mul(N, dim, rhs);
 #pragma unroll
-                                for (int c = 0; c < LB; ++c) w += B0[k * NU + li * LB + c] * Nj[c * LB + a];
-                                Bm[k * LB + a] = w;
-                            }
-                        }
-                    }
-                }
-                if (!factor()) break;
-                solve(xv);
+                for (int a = 0; a < LB; ++a)
+#pragma unroll
+                    for (int b = 0; b <= a; ++b) G[tri(a, b)] = (a == b) ? Rw(l, a) : 0.0;
+                if (!factor_stage<true>(v, r, G, rhs, pv, L::o_xv, N, dim)) pol = false;
+            }
+            bool changed = false;
+            {
+                double z[12];
+#pragma unroll
+                for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
-                for (int j = 0; j < S; ++j) {
-                    SV Nj = Nn + j * E;
-#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    stage_sync();
+                    if (!pol) continue;
+                    prefetch_rec(v + 1, L::REC);
+                    SV r = rec(v);
+                    double xs[LB], us[LB], up[LB];
+                    solve_fwd_stage<true>(v, r, L::o_xv, z, xs);
+#pragma unroll
                     for (int c = 0; c < LB; ++c) {
-                        double acc = ppv[j * LB + c];
+                        double acc = 0.0;
 #pragma unroll
-                        for (int a = 0; a < LB; ++a) acc += Nj[c * LB + a] * xv[j * LB + a];
-                        upv[j * LB + c] = acc;
+                        for (int a = 0; a < LB; ++a) acc += r[L::o_Nn + c * LB + a] * xs[a];
+                        us[c] = acc;
+                        up[c] = r[L::o_pp + c] + acc;
+                        r[L::o_u + c] = up[c];
                     }
-                }
-                // primal check: violated inactive rows join the active set
-                bool changed = false;
-#pragma unroll 1
-                for (int j = 0; j < S; ++j) {
-                    double vb[LB];
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) vb[c] = upv[j * LB + c];
-#pragma unroll 1
-                    for (int k = 0; k < mb; ++k) {
-                        const double bk = rb[k];
-                        const double viol = cdotr(k, vb) - bk;
-                        if (viol > 1e-9 * (1.0 + fabs(bk)) && !((amask[j] >> k) & 1)) amask[j] |= 1 << k, changed = true;
-                    }
-                }
-                if (changed) continue;
-                // dual check: minus the gradient must be a non-negative combination of the active rows
-                grad(upv, tvp, nullptr);
-                bool fail = false;
-#pragma unroll 1
-                for (int j = 0; j < S; ++j) {
-                    double rneg[LB], lam[L::MBM];
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) rneg[c] = -tvp[j * LB + c];
-                    for (int k = 0; k < mb; ++k) lam[k] = r_l[j * mb + k];
-                    unsigned drop = 0u;
-                    if (block_dual_fast<LB>(Cb, mb, (unsigned)amask[j], lam, rneg, gs)) continue;
-                    if (!block_dual_check<LB>(Cb, mb, (unsigned)amask[j], rneg, gs, &drop)) {
-                        if (drop == 0u) fail = true;
-                        else amask[j] &= ~(int)drop, changed = true;
-                    }
-                }
-                if (fail) break;
-                if (!changed) {
-                    polished = true;
-                    break;
+                    advance_z(v, r, us, z);
+                    // primal check: violated inactive rows join the active set
+                    unsigned mk = (unsigned)r[L::o_am];
+                    bool ch = false;
+                    for_rows([&](auto tag, int, int k) {
+                        const double bk = rrhs(tag);
+                        const double viol = rdot(tag, up) - bk;
+                        if (viol > 1e-9 * (1.0 + fabs(bk)) && !((mk >> k) & 1u)) mk |= 1u << k, ch = true;
+                    });
+                    if (ch) r[L::o_am] = (double)mk, changed = true;
                 }
             }
+            if (pol && !changed) {
+                // dual check: minus the gradient must be a non-negative combination of the active rows
+                grad(L::o_u, L::o_tv, nullptr);
+                bool fail = false;
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+                    double rneg[LB], lam[NR];
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) rneg[c] = -r[L::o_tv + c];
+                    for_rows([&](auto, int slot, int k) { lam[k] = r[L::o_l + slot]; });
+                    unsigned mk = (unsigned)r[L::o_am];
+                    unsigned drop = 0u;
+                    if (block_dual_fast<LB>(Cb, mb, mk, lam, rneg, gs)) continue;
+                    if (!block_dual_check<LB>(Cb, mb, mk, rneg, gs, &drop)) {
+                        if (drop == 0u) fail = true;
+                        else r[L::o_am] = (double)(mk & ~drop), changed = true;
+                    }
+                }
+                if (fail) pol = false;
+                else if (!changed) polished = true, pol = false;
+            }
         }
-        if (!polished) {
+        if (act && !polished) {
             io.status[inst] = 1;
             io.iters[inst] = it;
-            return;
+            act = false;
         }
+        if (!act) return;
 
         // ---- 4. outputs ----
         double u0[12];
         double umax = 0.0;
-        for (int e = 0; e < HZ * 12; ++e) {
-            const int s = e / 12, c12 = e - 12 * s;
-            const int l = (c12 % 6) / 3, comp = (c12 < 6) ? (c12 % 3) : (3 + c12 % 3);
-            const int b = blockOf[2 * s + l];
-            double val = 0.0;
-            if (b >= 0) {
-                val = p.lo6[comp];
-                for (int c = 0; c < LB; ++c)
-                    if (p.comps[c] == comp) val = upv[b * LB + c];
+#pragma unroll 1
+        for (int s = 0; s < HZ; ++s) {
+            double u12[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) u12[e] = 0.0;
+#pragma unroll
+            for (int li = 0; li < NF; ++li) {
+                const int v = s * NF + li, l = foot_of(v);
+                SV r = rec(v);
+                double up[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) up[c] = r[L::o_u + c];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {  // u = [f1 f2 m1 m2] (MPC.py:10)
+                    if (l) u12[3 + c] = up[c]; else u12[c] = up[c];
+                }
+                if (l) u12[9] = pin, u12[10] = up[3], u12[11] = up[4];
+                else u12[6] = pin, u12[7] = up[3], u12[8] = up[4];
             }
-            io.controls[(size_t)inst * HZ * 12 + e] = val;
-            umax = fmax(umax, fabs(val));
-            if (s == 0) u0[c12] = val;
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                io.controls[(size_t)inst * HZ * 12 + s * 12 + e] = u12[e];
+                umax = fmax(umax, fabs(u12[e]));
+                if (s == 0) u0[e] = u12[e];
+            }
         }
         const double uscale = fmax(1.0, umax);
-        if (io.states) grad(upv, tvp, io.states + (size_t)inst * HZ * 13);
+        if (io.states) grad(L::o_u, L::o_tv, io.states + (size_t)inst * HZ * 13);
         if (io.fric_active) {
+            const double tol = 1e-6 * uscale;
+#pragma unroll 1
             for (int s = 0; s < HZ; ++s) {
-                const double tol = 1e-6 * uscale;
                 unsigned mask = 0;
-                for (int l = 0; l < 2; ++l) {
-                    const int b = blockOf[2 * s + l];
-                    if (b < 0) continue;
-                    double f[3] = {p.lo6[0], p.lo6[1], p.lo6[2]};
-                    for (int c = 0; c < LB; ++c)
-                        if (p.comps[c] < 3) f[p.comps[c]] = upv[b * LB + c];
-                    if (f[2] <= tol) continue;
-                    const double res[4] = {f[0] - p.mu * f[2], f[1] - p.mu * f[2], -f[0] - p.mu * f[2], -f[1] - p.mu * f[2]};
-                    for (int r = 0; r < 4; ++r)
-                        if (res[r] >= -tol) mask |= 1u << (4 * l + r);
+#pragma unroll
+                for (int li = 0; li < NF; ++li) {
+                    const int v = s * NF + li, l = foot_of(v);
+                    SV r = rec(v);
+                    const double f0 = r[L::o_u + 0], f1 = r[L::o_u + 1], f2 = r[L::o_u + 2];
+                    if (f2 <= tol) continue;
+                    const double res[4] = {f0 - p.mu * f2, f1 - p.mu * f2, -f0 - p.mu * f2, -f1 - p.mu * f2};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (res[q] >= -tol) mask |= 1u << (4 * l + q);
                 }
                 io.fric_active[(size_t)inst * HZ + s] = (uint8_t)mask;
             }
         }
         if (io.do_lowlevel && io.tau) {
-            double q[10], qd[10], pf[6];
+            double q[10], qd[10], pf[6], x_fb[12], rotn[9];
+            for (int a = 0; a < 12; ++a) x_fb[a] = xfb[a];
+            eul2rotm(x_fb, rotn);
             for (int a = 0; a < 10; ++a) q[a] = io.q[(size_t)inst * 10 + a], qd[a] = io.qd[(size_t)inst * 10 + a];
             for (int a = 0; a < 6; ++a) pf[a] = io.pf_w[(size_t)inst * 6 + a];
             for (int leg = 0; leg < 2; ++leg) {
                 double tl[5];
-                lowlevel_leg(p, x_fb, io.t_swing[inst], pf, q, qd, rotn, leg, (double)cont0[leg], u0, tl);
+                lowlevel_leg_inl(p, x_fb, io.t_swing[inst], pf, q, qd, rotn, leg, (double)cont0[leg], u0, tl);
                 for (int c = 0; c < 5; ++c) io.tau[(size_t)inst * 10 + 5 * leg + c] = tl[c];
             }
         }
-        if (io.ws_mask)
-            for (int e = 0; e < 2 * HZ; ++e) io.ws_mask[(size_t)inst * 2 * HZ + e] = blockOf[e] >= 0 ? amask[blockOf[e]] : -1;
+        if (io.ws_mask) {
+#pragma unroll 1
+            for (int s = 0; s < HZ; ++s) {
+                int m2[2] = {-1, -1};
+#pragma unroll
+                for (int li = 0; li < NF; ++li) {
+                    const int v = s * NF + li;
+                    const int mk = (int)rec(v)[L::o_am];
+                    if (foot_of(v)) m2[1] = mk; else m2[0] = mk;
+                }
+                io.ws_mask[(size_t)inst * 2 * HZ + 2 * s] = m2[0];
+                io.ws_mask[(size_t)inst * 2 * HZ + 2 * s + 1] = m2[1];
+            }
+        }
         io.status[inst] = 0;
         io.iters[inst] = it;
         if (io.resid) io.resid[2 * inst] = 0.0, io.resid[2 * inst + 1] = rdmax;
@@ -1065,31 +1308,38 @@ struct LaneSolver {
 };
 
 #if defined(__CUDACC__) && !defined(BMPC_LANE_HOST_ONLY)
-// One warp = 32 robots of the class's work list at a time (dynamic: a global counter hands out 32-robot slices).
-#ifndef BMPC_LANE_MINB
-#define BMPC_LANE_MINB 3
-#endif
-template <int HZ, int NF, int LB>
-__global__ void __launch_bounds__(128, BMPC_LANE_MINB) lane_tick_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
-                                                        const int* __restrict__ work_list, const int* __restrict__ work_count,
-                                                        int* __restrict__ slice_counter, double* __restrict__ wsbase, int min_count) {
-    using L = LaneL<HZ, NF, LB>;
-    const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Work distribution: a global counter hands out slices of the class's work list - 32 robots per warp when the warps run
+// independently (p.lane_sync == 0), 32 x (warps per CTA) robots per CTA when they run in lockstep.
+// Dynamic shared memory: per warp the packed cost-to-go of its 32 robots (78 x 32 doubles).
+template <int HZ, int NF, unsigned RM>
+__global__ void __launch_bounds__(256, 1) lane_tick_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
+                                                           const int* __restrict__ work_list, const int* __restrict__ work_count,
+                                                           int* __restrict__ slice_counter, double* __restrict__ wsbase, int min_count) {
+    using L = LaneRec<HZ, NF>;
+    extern __shared__ double lane_smem[];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int warp = blockIdx.x * nw + wib;
     const int count = *work_count;
-    // a class too small to fill the machine with 32-robot slices is faster on the warp-per-robot kernel (one slice takes
-    // ~20 ms whatever the batch): leave it alone, collect_or_all_kernel then hands the whole list over
+    // a class too small to be worth 32-robot slices stays on the warp-per-robot kernel: collect_or_all_kernel hands the whole list over
     if (count < min_count) return;
     SV ws{wsbase + (size_t)warp * L::total * 32 + lane};
+    SV ps{lane_smem + (size_t)wib * L::smem_doubles * 32 + lane};
     while (true) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(slice_counter, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        if (base + lane < count) {
-            LaneSolver<HZ, NF, LB> solver(p, ws);
-            solver.run(io, work_list[base + lane]);
+        if (p.lane_sync) {
+            __syncthreads();  // (everybody has read s_base of the previous round)
+            if (threadIdx.x == 0) s_base = atomicAdd(slice_counter, 32 * nw);
+            __syncthreads();
+            base = s_base + 32 * wib;
+            if (s_base >= count) break;
+        } else {
+            if (lane == 0) base = atomicAdd(slice_counter, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= count) break;
         }
+        LaneSolver<HZ, NF, true, RM> solver(p, ws, ps, lane);
+        solver.run(io, base + lane < count ? work_list[base + lane] : -1);
         __syncwarp();
     }
 }

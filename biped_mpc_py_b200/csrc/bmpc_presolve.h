@@ -33,19 +33,15 @@ inline int build_dev_params_impl(const bmpc_params& P, DevParams& d, std::string
     d.mu_tol = P.mu_tol > 0 ? P.mu_tol : 1e-7;
     d.rd_tol = P.rd_tol > 0 ? P.rd_tol : 10.0;
     d.gondzio = 1;
-    {
-        const char* eg = getenv("BMPC_GONDZIO_BELOW");  // run the centrality corrector only when the step length is below this
-        d.gondzio_below = eg ? atof(eg) : 0.95;  // measured: 1.722 M solves/s at 0.95 vs 1.696 M always (131,072 robots)
-    }
+    d.gondzio_below = 0.95;  // centrality corrector only when the step length is below this: 1.722 M solves/s vs 1.696 M always (131,072 robots)
     d.init_fz_frac = 0.2;   // start point: 20 % of the fz range, friction/moment components centred
     d.mu0_scale = 0.1;      // initial complementarity = mu0_scale * mean slack
     // polish rounds per attempt: long horizons have more weakly active rows that only show up as violations
     // one round at a time (h = 30 instances needing 5-7 rounds were measured with tools/kernel_model.py)
     d.polish_rounds = P.h > 10 ? 16 : 4;
-    {
-        const char* el = getenv("BMPC_LOCK");  // experiment knob: 3 = lockstep (default), 0 = with an extra step at instance start, 2 = none
-        d.lock_mode = el ? atoi(el) : 3;
-    }
+    d.lock_mode = 3;        // loose lockstep of the robots of a CTA (bmpc_tick.cuh)
+    d.lane_prefetch = 1;
+    d.lane_sync = 2;
     d.warm_rounds = 6;      // polish rounds allowed to a warm-started tick before it falls back to the cold path
     d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
     memcpy(d.x_cmd, P.x_cmd, sizeof(d.x_cmd));

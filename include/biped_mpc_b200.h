@@ -138,6 +138,21 @@ int bmpc_debug_assemble(bmpc_handle* h,
                         const double* x_fb, const int32_t* phase_k, const double* foot, const uint8_t* contact,
                         double* Hc_out, double* g_out, int32_t* n_out, void* stream);
 
+/* Tunables of the kernel dispatch (integers; the defaults need no call).  They replace the environment
+ * variables of earlier builds; results are the same certified optimum under every setting.
+ *   "lane_mode"         2 (default) the lane-per-robot kernels take both instance classes of throughput
+ *                       batches, 1 the walking class only, 0 warp-per-robot kernels only
+ *   "lane_min"          overrides the three size gates of the lane-per-robot kernels (batch and class sizes
+ *                       below which a class stays on the warp-per-robot kernel); -1 restores the defaults
+ *   "lane_ctas_per_sm"  resident CTAs per SM of the lane-per-robot kernels (0 / -1: as many as fit)
+ *   "lane_warps"        warps (32 robots each) per CTA of the lane-per-robot kernels (default 4)
+ *   "lane_prefetch"     0 disables the bulk L2 prefetch of the lane-per-robot kernels (measurement only)
+ *   "lane_sync"         lockstep of the warps of a lane-kernel CTA: 2 (default) barrier per stage of every sweep,
+ *                       1 per iteration, 0 independent warps (measurement only)
+ *   "lowlat"            0 disables the 128-thread low-latency kernel used for batches <= 8
+ * Synchronises the device (the lane workspace is re-sized). */
+int bmpc_set_option(bmpc_handle* h, const char* name, int value);
+
 /* Number of kernels this handle has launched so far (for bench.py's gpu_launches). */
 int64_t bmpc_launch_count(const bmpc_handle* h);
 

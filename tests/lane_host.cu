@@ -5,8 +5,27 @@
 
 #include "../biped_mpc_py_b200/csrc/bmpc_presolve.h"
 #include "../biped_mpc_py_b200/csrc/bmpc_lane.cuh"
+#include "../biped_mpc_py_b200/csrc/bmpc_lane_api.h"
 
 using namespace bmpc;
+
+template <int HZ, int NF, unsigned RM>
+static void run_rm(const DevParams& d, std::vector<double>& w, std::vector<double>& ps, const IoPtrs& io, int i, bool f32) {
+    if (f32) LaneSolver<HZ, NF, true, RM>(d, SV{w.data()}, SV{ps.data()}, 0).run(io, i);
+    else LaneSolver<HZ, NF, false, RM>(d, SV{w.data()}, SV{ps.data()}, 0).run(io, i);
+}
+// same choice as bmpc_lane.cu: the instantiation specialised for the presolve's row set if there is one, else the generic one
+template <int HZ, int NF>
+static void run_one(const DevParams& d, std::vector<double>& w, std::vector<double>& ps, const IoPtrs& io, int i, bool f32) {
+    const unsigned rm = lane_rowmask(d);
+    if (rm == kRowsRef) run_rm<HZ, NF, kRowsRef>(d, w, ps, io, i, f32);
+    else if (rm == kRowsSym) run_rm<HZ, NF, kRowsSym>(d, w, ps, io, i, f32);
+    else run_rm<HZ, NF, 0u>(d, w, ps, io, i, f32);
+}
+
+// factor storage of the interior point: 1 = float (what the GPU kernels run), 0 = double (numerical reference for the tests)
+static int g_f32 = 1;
+extern "C" void lane_host_set_f32(int on) { g_f32 = on; }
 
 extern "C" int lane_host_tick(const bmpc_params* P, int n, const double* x_fb, const int32_t* phase_k, const double* t_swing,
                               const double* foot, const uint8_t* contact, const double* q, const double* qd, const double* pf_w,
@@ -20,16 +39,16 @@ extern "C" int lane_host_tick(const bmpc_params* P, int n, const double* x_fb, c
     io.x_fb = x_fb, io.phase_k = phase_k, io.t_swing = t_swing, io.foot = foot, io.contact = contact, io.q = q, io.qd = qd,
     io.pf_w = pf_w, io.controls = controls, io.states = states, io.tau = tau, io.status = status, io.iters = iters,
     io.fric_active = fric_active, io.resid = resid, io.ws_mask = ws_mask, io.do_lowlevel = 1;
-    std::vector<double> w1(LaneL<30, 1, 5>::total), w2(LaneL<30, 2, 5>::total);
+    std::vector<double> w1(LaneRec<30, 1>::total), w2(LaneRec<30, 2>::total), ps(LaneRec<30, 2>::smem_doubles);
     for (int i = 0; i < n; ++i) {
         int S = 0;
         for (int k = 0; k < 2 * d.h; ++k) S += contact[(size_t)i * 2 * d.h + k] ? 1 : 0;
         if (d.h == 10) {
-            if (S <= 10) LaneSolver<10, 1, 5>(d, SV{w1.data()}).run(io, i);
-            else LaneSolver<10, 2, 5>(d, SV{w2.data()}).run(io, i);
+            if (S <= 10) run_one<10, 1>(d, w1, ps, io, i, g_f32 != 0);
+            else run_one<10, 2>(d, w2, ps, io, i, g_f32 != 0);
         } else {
-            if (S <= 30) LaneSolver<30, 1, 5>(d, SV{w1.data()}).run(io, i);
-            else LaneSolver<30, 2, 5>(d, SV{w2.data()}).run(io, i);
+            if (S <= 30) run_one<30, 1>(d, w1, ps, io, i, g_f32 != 0);
+            else run_one<30, 2>(d, w2, ps, io, i, g_f32 != 0);
         }
     }
     return 0;

@@ -21,10 +21,17 @@ def torch_cuda():
     return torch
 
 
-def _solver(variant=0, max_batch=256, **kw):
+def _solver(variant=0, max_batch=256, lane=None, **kw):
+    """lane=None: default dispatch (size gates decide); "force": the lane-per-robot kernels take every class whatever
+    its size (bmpc_set_option lane_min = 1); "off": warp-per-robot kernels only."""
     from biped_mpc_py_b200 import BatchedMPC
     mpc, biped = variant_params(variant)
-    return BatchedMPC(mpc, biped, max_batch=max_batch, **kw), mpc, biped
+    solver = BatchedMPC(mpc, biped, max_batch=max_batch, **kw)
+    if lane == "force":
+        solver.set_option("lane_min", 1)
+    elif lane == "off":
+        solver.set_option("lane_mode", 0)
+    return solver, mpc, biped
 
 
 def test_library_loaded_and_no_fallback(torch_cuda):
@@ -56,12 +63,14 @@ def test_assembly_matches_model(torch_cuda, golden):
         solver.close()
 
 
-def test_golden_cases_from_reference(torch_cuda, golden):
-    """Every fixture case (reference assembly + exact optimum + reference lowLevelControl)."""
+@pytest.mark.parametrize("lane", [None, "force"])
+def test_golden_cases_from_reference(torch_cuda, golden, lane):
+    """Every fixture case (reference assembly + exact optimum + reference lowLevelControl); once through the default
+    dispatch (small batch: warp-per-robot kernels) and once with the lane-per-robot kernels forced on."""
     g = golden
     for variant in (0, 1, 2):
         idx = np.nonzero(g["variant"] == variant)[0]
-        solver, mpc, biped = _solver(variant, max_batch=len(idx))
+        solver, mpc, biped = _solver(variant, max_batch=len(idx), lane=lane)
         out = solver.step_host(g["x_fb"][idx], g["t"][idx], g["pf_w"][idx], g["contact"][idx], g["q"][idx],
                                g["qd"][idx], g["pf_w"][idx], want_states=True)
         assert (out["status"] == 0).all(), out["status"]
@@ -123,16 +132,32 @@ def test_random_batch_against_oracle(torch_cuda):
     solver.close()
 
 
-def test_config1_4096_instances_each_against_oracle(torch_cuda):
-    """BASELINE.json configs[1]: 4,096 independent horizon-10 QPs from randomised states on one B200, EVERY instance
-    checked against the oracle's certified optimum (the oracle runs on all host cores, ~40 ms per instance)."""
+_ORACLE_4096 = {}
+
+
+def _oracle_4096():
+    """oracle answers of the configs[1] batch, computed once for both dispatch modes (all host cores, ~40 ms per instance)"""
     from biped_mpc_py_b200 import synth
     from oracle_pool import oracle_parallel
+    if not _ORACLE_4096:
+        mpc, biped = variant_params(0)
+        batch = synth.make_batch(4096, shard_index=2, mpc=mpc, biped=biped)
+        _ORACLE_4096["batch"] = batch
+        _ORACLE_4096["UTM"] = oracle_parallel(batch, 4096)
+    return _ORACLE_4096["batch"], _ORACLE_4096["UTM"]
+
+
+@pytest.mark.parametrize("lane", ["force", None])
+def test_config1_4096_instances_each_against_oracle(torch_cuda, lane):
+    """BASELINE.json configs[1]: 4,096 independent horizon-10 QPs from randomised states on one B200, EVERY instance
+    checked against the oracle's certified optimum - through the lane-per-robot kernels (the kernels that run the throughput
+    batches; forced on here because 4,096 robots are below their size gates) and through the default dispatch."""
     n = 4096
-    solver, mpc, biped = _solver(0, max_batch=n)
-    batch = synth.make_batch(n, shard_index=2, mpc=mpc, biped=biped)
+    batch, (U, T, M) = _oracle_4096()
+    solver, mpc, biped = _solver(0, max_batch=n, lane=lane)
+    launches0 = solver.launch_count
     out = solver.step_host(batch["x_fb"], batch["t"], batch["foot"], batch["contact"], batch["q"], batch["qd"], batch["pf_w"])
-    U, T, M = oracle_parallel(batch, n)
+    assert solver.launch_count - launches0 == (7 if lane == "force" else 3)  # classify + 2 x (lane, collect, warp-per-robot) | classify + 2
     assert (out["status"] == 0).all(), np.bincount(out["status"])
     scale = np.maximum(1.0, np.abs(U).reshape(n, -1).max(axis=1))
     du = np.abs(out["controls"] - U).reshape(n, -1).max(axis=1) / scale
@@ -150,6 +175,8 @@ def test_config1_4096_instances_each_against_oracle(torch_cuda):
             near = near or (np.abs(res + tol) < 10 * tol).any() or abs(fz - tol) < 10 * tol
         assert near, (i, s, out["fric_active"][i, s], M[i, s])
         n_differ += 1
+    print(f"[parity lane={lane}] 4096 instances: max rel |du| {du.max():.2e}, max |dtau| {dtau.max():.2e} N*m, "
+          f"{n_differ} of {M.size} (instance, stage) friction masks differ, all within 10x the activity threshold")
     assert n_differ <= n // 100
     solver.close()
 
@@ -187,6 +214,20 @@ def test_device_api_matches_host_api_and_is_shard_invariant(torch_cuda):
     pf = solver.foot_positions(tn(b["x_fb"]), tn(b["q"]))
     np.testing.assert_allclose(pf.cpu().numpy(), b["pf_w"], rtol=0, atol=1e-14)
     solver.close()
+
+
+def test_foot_positions_kernel_against_reference_fixture(torch_cuda, golden):
+    """Batched forward kinematics on the GPU (foot_positions_kernel) against pf_w of the fixture cases, which
+    oracle/gen_golden.py computed with the REAL reference's getFootPositionWorld (MPC.py:406-424)."""
+    torch = torch_cuda
+    g = golden
+    for variant in (0, 1, 2):
+        idx = np.nonzero(g["variant"] == variant)[0]
+        solver, mpc, biped = _solver(variant, max_batch=len(idx))
+        tn = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=solver.device)
+        pf = solver.foot_positions(tn(g["x_fb"][idx]), tn(g["q"][idx])).cpu().numpy()
+        np.testing.assert_allclose(pf, g["pf_w"][idx], rtol=0, atol=1e-13)
+        solver.close()
 
 
 def test_reference_signatures_known_answers(torch_cuda):
@@ -292,11 +333,11 @@ def test_mixed_contact_patterns(torch_cuda):
     solver.close()
 
 
-def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
+def test_lane_per_robot_front_end_matches_default_path(torch_cuda):
     """The lane-per-robot kernels (csrc/bmpc_lane.cuh; one thread per robot, front end of both classes when a class has enough
-    robots to fill the machine - BMPC_LANE_MIN=1 removes that gate here; everything they do not certify falls through to the
-    warp-per-robot kernels) must return the same certified optimum as the warp-per-robot kernels alone (BMPC_LANE=0):
-    synthetic batch + arbitrary contact schedules (those are not the lane path's and exercise the fall-through)."""
+    robots - lane_min = 1 removes that gate here; everything they do not certify falls through to the warp-per-robot kernels)
+    must return the same certified optimum as the warp-per-robot kernels alone (lane_mode = 0): synthetic batch + arbitrary
+    contact schedules (those are not the lane path's and exercise the fall-through)."""
     from biped_mpc_py_b200 import synth
     n = 2048
     mpc, biped = variant_params(0)
@@ -305,15 +346,12 @@ def test_lane_per_robot_front_end_matches_default_path(torch_cuda, monkeypatch):
     b["contact"][:64] = (rng.uniform(size=(64, 10, 2)) < 0.6).astype(np.uint8)
     b["x_fb"][64, 1] = np.nan  # bad input must still be flagged through the fall-through
     args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
-    monkeypatch.setenv("BMPC_LANE", "0")  # warp-per-robot kernels only
-    ref_solver, _, _ = _solver(0, max_batch=n)
+    ref_solver, _, _ = _solver(0, max_batch=n, lane="off")  # warp-per-robot kernels only
     launches0 = ref_solver.launch_count
     ref = ref_solver.step_host(*args, want_states=True)
     assert ref_solver.launch_count - launches0 == 3
     ref_solver.close()
-    monkeypatch.setenv("BMPC_LANE", "2")  # 1: walking class only, 2: both classes
-    monkeypatch.setenv("BMPC_LANE_MIN", "1")
-    lane_solver, _, _ = _solver(0, max_batch=n)
+    lane_solver, _, _ = _solver(0, max_batch=n, lane="force")
     launches0 = lane_solver.launch_count
     out = lane_solver.step_host(*args, want_states=True)
     assert lane_solver.launch_count - launches0 == 7  # classify + 2 x (lane, collect, warp-per-robot)

@@ -108,7 +108,7 @@ def test_h30_unpinned_limit_set_lb6():
     s.close()
 
 
-def test_h30_lane_per_robot_front_end_matches_warp_kernels(monkeypatch):
+def test_h30_lane_per_robot_front_end_matches_warp_kernels():
     """h = 30 through the lane-per-robot kernels (size gates removed) against the warp-per-robot kernels alone."""
     import numpy as np
     from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
@@ -116,13 +116,12 @@ def test_h30_lane_per_robot_front_end_matches_warp_kernels(monkeypatch):
     mpc, biped = MPC(h=30), Biped()
     b = synth.make_batch(n, shard_index=31, mpc=mpc, biped=biped, extend=True)
     args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
-    monkeypatch.setenv("BMPC_LANE", "0")
     ref_solver = BatchedMPC(mpc, biped, max_batch=n, extend_gait=True)
+    ref_solver.set_option("lane_mode", 0)
     ref = ref_solver.step_host(*args, phase_k=b["phase_k"])
     ref_solver.close()
-    monkeypatch.setenv("BMPC_LANE", "2")
-    monkeypatch.setenv("BMPC_LANE_MIN", "1")
     lane_solver = BatchedMPC(mpc, biped, max_batch=n, extend_gait=True)
+    lane_solver.set_option("lane_min", 1)
     out = lane_solver.step_host(*args, phase_k=b["phase_k"])
     lane_solver.close()
     assert (ref["status"] == 0).all() and (out["status"] == 0).all()
