@@ -242,7 +242,20 @@ struct LaneSolver {
         return r;
     }
     // -dv / v in FP32: only a step LENGTH, cut by step_frac afterwards; NaN/Inf propagate
-    static BMPC_HD __forceinline__ float sratio(double dv, double v) { return -(float)dv / (float)v; }
+    static BMPC_HD __forceinline__ float sratio(double dv, double v) {
+#ifdef __CUDA_ARCH__
+        return __fdividef(-(float)dv, (float)v);  // (no slow-path branch: the rows of a block stay in one basic block)
+#else
+        return -(float)dv / (float)v;
+#endif
+    }
+    // the stored slacks and multipliers of a block, loaded up front so that their latency overlaps instead of adding up row by row
+    BMPC_HD __forceinline__ void load_rows(SV r, double (&sv)[NR], double (&lv)[NR]) const {
+        for_rows([&](auto, int slot, int) {
+            sv[slot] = r[L::o_s + slot];
+            lv[slot] = r[L::o_l + slot];
+        });
+    }
 
     // ---- structural input map: column c of B_v is [B3[0..2][c]; vm e_c (c < 3)] on the (omega, v) rows ----------------
     BMPC_HD __forceinline__ void load_B3(SV r, double (&B3)[3][LB]) const {
@@ -656,6 +669,47 @@ struct LaneSolver {
         B_mul_add(B3, ustep, z + 6);
     }
 
+    // ---- the row pass of sweep A for one block: (APPLY) the previous iteration's step in u, s, lam and rd, recomputed from the
+    //      stored step vectors; then barrier weights, the predictor right-hand side (accumulated into gacc, which enters holding
+    //      rd) and the block's input weights G.  Returns the block's complementarity sum. -----------------------------------
+    template <bool APPLY>
+    BMPC_HD __forceinline__ double rows_A(SV r, double alpha, double tgt, const double (&u)[LB], double (&gacc)[LB], double (&G)[15]) const {
+        double sv[NR], lv[NR], x5[LB], d5[LB];
+        load_rows(r, sv, lv);
+        if constexpr (APPLY) {
+#pragma unroll
+            for (int c = 0; c < LB; ++c) {
+                x5[c] = r[L::o_xv + c];
+                d5[c] = r[L::o_du + c];
+                gacc[c] *= (1.0 - alpha);
+                r[L::o_rd + c] = gacc[c];
+                r[L::o_u + c] = u[c] + alpha * d5[c];
+            }
+        }
+        double part = 0.0;
+        for_rows([&](auto tag, int slot, int) {
+            double s = sv[slot], lm = lv[slot];
+            const double b = rrhs(tag);
+            double cu = rdot(tag, u);
+            if constexpr (APPLY) {
+                const double cx = rdot(tag, x5), cd = rdot(tag, d5);
+                RowStep q = row_affine(cu, cx, s, lm, b);
+                const double wc = (q.dsa * q.dla - tgt) * q.is;
+                const double ds = -q.rp - cd, dl = -lm - wc - q.d * ds;
+                s += alpha * ds;
+                lm += alpha * dl;
+                cu += alpha * cd;
+                r[L::o_s + slot] = s;
+                r[L::o_l + slot] = lm;
+            }
+            const double d = lm * rcp_nr(s), rp = cu + s - b;
+            part += s * lm;
+            radd(tag, gacc, d * rp - lm);
+            rrank(tag, G, d);
+        });
+        return part;
+    }
+
     // ---- group synchronisation: the warps of a CTA can run in lockstep (p.lane_sync: 0 none, 1 per iteration / phase, 2 also per
     //      stage of every sweep) so that they fetch the same instructions at the same time.  Every thread of the group takes
     //      the same control path; `act`-style flags, not returns, switch a lane off. ------------------------------------
@@ -884,48 +938,18 @@ struct LaneSolver {
                 prefetch_rec(v - 1, L::o_Y);
                 SV r = rec(v);
                 const int l = foot_of(v);
-                double u[LB], gacc[LB], G[15], x5[LB], d5[LB];
+                double u[LB], gacc[LB], G[15];
 #pragma unroll
                 for (int c = 0; c < LB; ++c) {
                     u[c] = r[L::o_u + c];
                     gacc[c] = r[L::o_rd + c];
-                    x5[c] = d5[c] = 0.0;
-                }
-                const bool apply = alpha != 0.0;  // (du is not initialised before the first step)
-                if (apply) {
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) {
-                        x5[c] = r[L::o_xv + c];
-                        d5[c] = r[L::o_du + c];
-                        gacc[c] *= (1.0 - alpha);
-                        r[L::o_rd + c] = gacc[c];
-                        r[L::o_u + c] = u[c] + alpha * d5[c];
-                    }
                 }
 #pragma unroll
                 for (int a = 0; a < LB; ++a)
 #pragma unroll
                     for (int b = 0; b <= a; ++b) G[tri(a, b)] = (a == b) ? Rw(l, a) : 0.0;
-                for_rows([&](auto tag, int slot, int) {
-                    double s = r[L::o_s + slot], lm = r[L::o_l + slot];
-                    const double b = rrhs(tag);
-                    double cu = rdot(tag, u);
-                    if (apply) {
-                        const double cx = rdot(tag, x5), cd = rdot(tag, d5);
-                        RowStep q = row_affine(cu, cx, s, lm, b);
-                        const double wc = (q.dsa * q.dla - tgt) * q.is;
-                        const double ds = -q.rp - cd, dl = -lm - wc - q.d * ds;
-                        s += alpha * ds;
-                        lm += alpha * dl;
-                        cu += alpha * cd;
-                        r[L::o_s + slot] = s;
-                        r[L::o_l + slot] = lm;
-                    }
-                    const double d = lm * rcp_nr(s), rp = cu + s - b;
-                    part += s * lm;
-                    radd(tag, gacc, d * rp - lm);
-                    rrank(tag, G, d);
-                });
+                if (alpha != 0.0) part += rows_A<true>(r, alpha, tgt, u, gacc, G);
+                else part += rows_A<false>(r, alpha, tgt, u, gacc, G);  // first iteration: no step to apply (du is not initialised yet)
                 double rhs[LB];
 #pragma unroll
                 for (int c = 0; c < LB; ++c) rhs[c] = -gacc[c];
@@ -945,16 +969,16 @@ struct LaneSolver {
                     if (!ipm) continue;
                     prefetch_rec(v + 1, L::o_Y + kFacDoubles);
                     SV r = rec(v);
-                    double xs[LB], u[LB];
+                    double xs[LB], u[LB], sv[NR], lv[NR];
+                    load_rows(r, sv, lv);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) u[c] = r[L::o_u + c];
                     solve_fwd_stage<false>(v, r, L::o_xv, z, xs);
 #pragma unroll
-                    for (int c = 0; c < LB; ++c) {
-                        r[L::o_xv + c] = xs[c];
-                        u[c] = r[L::o_u + c];
-                    }
+                    for (int c = 0; c < LB; ++c) r[L::o_xv + c] = xs[c];
                     advance_z(v, r, xs, z);
                     for_rows([&](auto tag, int slot, int) {
-                        const double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                        const double s = sv[slot], lm = lv[slot];
                         const RowStep q = row_affine(rdot(tag, u), rdot(tag, xs), s, lm, rrhs(tag));
                         ratio = fmaxf(ratio, fmaxf(sratio(q.dsa, s), sratio(q.dla, lm)));
                         part += q.dsa * q.dla;
@@ -977,7 +1001,8 @@ struct LaneSolver {
                 if (!ipm) continue;
                 prefetch_rec(v - 1, L::o_Y + kFacDoubles);
                 SV r = rec(v);
-                double u[LB], x5[LB], gacc[LB];
+                double u[LB], x5[LB], gacc[LB], sv[NR], lv[NR];
+                load_rows(r, sv, lv);
 #pragma unroll
                 for (int c = 0; c < LB; ++c) {
                     u[c] = r[L::o_u + c];
@@ -985,7 +1010,7 @@ struct LaneSolver {
                     gacc[c] = 0.0;
                 }
                 for_rows([&](auto tag, int slot, int) {
-                    const double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                    const double s = sv[slot], lm = lv[slot];
                     const RowStep q = row_affine(rdot(tag, u), rdot(tag, x5), s, lm, rrhs(tag));
                     radd(tag, gacc, (q.dsa * q.dla - tgt) * q.is);
                 });
@@ -1004,18 +1029,22 @@ struct LaneSolver {
                     if (!ipm) continue;
                     prefetch_rec(v + 1, L::o_Y + kFacDoubles);
                     SV r = rec(v);
-                    double xs[LB], u[LB], x5[LB], d5[LB];
-                    solve_fwd_stage<false>(v, r, L::o_du, z, xs);
-                    advance_z(v, r, xs, z);
+                    double xs[LB], u[LB], x5[LB], d5[LB], sv[NR], lv[NR];
+                    load_rows(r, sv, lv);
 #pragma unroll
                     for (int c = 0; c < LB; ++c) {
                         u[c] = r[L::o_u + c];
                         x5[c] = r[L::o_xv + c];
+                    }
+                    solve_fwd_stage<false>(v, r, L::o_du, z, xs);
+                    advance_z(v, r, xs, z);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) {
                         d5[c] = xs[c] + x5[c];
                         r[L::o_du + c] = d5[c];
                     }
                     for_rows([&](auto tag, int slot, int) {
-                        const double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                        const double s = sv[slot], lm = lv[slot];
                         const RowStep q = row_affine(rdot(tag, u), rdot(tag, x5), s, lm, rrhs(tag));
                         const double wc = (q.dsa * q.dla - tgt) * q.is;
                         const double ds = -q.rp - rdot(tag, d5), dl = -lm - wc - q.d * ds;
