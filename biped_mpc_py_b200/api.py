@@ -99,8 +99,9 @@ class BatchedMPC:
         _lib.check(self._lib.bmpc_enable_timing(self._h, int(on)))
 
     def last_timing_ms(self):
-        """(classify, walking-class kernel, standing-class kernel) device times of the last tick."""
-        ms = (ctypes.c_float * 3)()
+        """(classify, lane-per-robot kernel, walking-class warp-per-robot kernel, standing-class warp-per-robot kernel)
+        device times of the last tick in ms."""
+        ms = (ctypes.c_float * 4)()
         _lib.check(self._lib.bmpc_last_timing(self._h, ms))
         return [float(v) for v in ms]
 

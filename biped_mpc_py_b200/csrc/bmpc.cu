@@ -92,7 +92,11 @@ struct bmpc_handle {
     int warm_enabled = 0;        // bmpc_warm_start: bmpc_step / bmpc_solve start from the previous call's active set
     int warm_valid = 0;          // the store holds the masks of a previous call
     int timing = 0;              // record CUDA events around each kernel of a tick
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // the two lane-per-robot class kernels run concurrently: the standing class on the caller's stream, the walking class on
+    // this side stream, so that the classes share one tail instead of each paying its own
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
 };
 
 namespace {
@@ -156,26 +160,51 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    const bool use_lane = n >= h->lane_min && !io.warm && (h->lane[0].fn || h->lane[1].fn);
+    if (use_lane) {
+        // throughput batches: one THREAD per robot first (32 robots share every instruction); robots it does not certify
+        // (status 1) are collected below and solved by the warp-per-robot kernels.  The standing class (twice the work per
+        // robot, usually the smaller class) is launched first; the walking class follows on the side stream and fills the SMs
+        // as the standing CTAs run out of slices.
+        const bool both = h->lane[0].fn && h->lane[1].fn;
+        if (both) {
+            if (!h->side) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming));
+            }
+            CUDA_TRY(cudaEventRecord(h->fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(h->side, h->fork, 0));
+        }
+        for (int b = 1; b >= 0; --b) {
+            LaneVariant& lv = h->lane[b];
+            if (!lv.fn) continue;
+            if (!lv.d_ws) CUDA_TRY(cudaMalloc(&lv.d_ws, sizeof(double) * lv.ws_doubles));
+            cudaStream_t ls = (both && b == 0) ? h->side : st;
+            lv.fn<<<std::min(lv.grid, (n + lv.threads - 1) / lv.threads), lv.threads, lv.smem, ls>>>(
+                h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b, h->d_counts + 12 + b, lv.d_ws, lv.min_count);
+            h->launches += 1;
+        }
+        if (both) {
+            CUDA_TRY(cudaEventRecord(h->join, h->side));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->join, 0));
+        }
+    }
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2], st));
     for (int b = 0; b < 2; ++b) {
         // real-time use (N = 1 .. 8): every walking robot gets a whole 128-thread CTA (0.26 ms instead of 0.32 ms for one
         // robot end to end).  Same optimum, but reductions run in a different order, so results of batches <= 8 may
-        // differ in the last bits from the throughput kernel; every larger batch is bit-identical under any split.
+        // differ in the last bits from the throughput kernel.
         const Variant& v = (b == 0 && h->lowlat.fn && h->opt_lowlat != 0 && n <= 8) ? h->lowlat : h->bucket[b];
         // persistent thread groups: as many as fit on the device, each strides over its bucket's work list
         const int grid = (std::min(n, v.resident) + v.per_cta - 1) / v.per_cta;
         const int* list = h->d_lists + (size_t)b * h->max_batch;
         const int* cnt = h->d_counts + b;
-        if (h->lane[b].fn && n >= h->lane_min && !io.warm) {
-            // throughput batches: one THREAD per robot first (32 robots share every instruction); robots it does not
-            // certify (status 1) are collected and solved by the warp-per-robot kernel below
+        if (use_lane && h->lane[b].fn) {
             int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
-            if (!h->lane[b].d_ws) CUDA_TRY(cudaMalloc(&h->lane[b].d_ws, sizeof(double) * h->lane[b].ws_doubles));
-            const LaneVariant& lv = h->lane[b];
-            lv.fn<<<std::min(lv.grid, (n + lv.threads - 1) / lv.threads), lv.threads, lv.smem, st>>>(h->dp, io, list, cnt, h->d_counts + 12 + b,
-                                                                                                      lv.d_ws, lv.min_count);
             collect_or_all_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b, h->lane[b].min_count);
             list = rlist, cnt = h->d_counts + 6 + b;
-            h->launches += 2;
+            h->launches += 1;
         }
         v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, list, cnt, v.d_scratch);
         if (b == 1 && h->fallback.fn) {
@@ -188,7 +217,7 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
             f.fn<<<fgrid, f.threads, f.smem, st>>>(h->dp, io, h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2, f.d_scratch);
             h->launches += 3;
         }
-        if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2 + b], st));
+        if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[3 + b], st));
     }
     h->launches += 3;
     CUDA_TRY(cudaGetLastError());
@@ -336,8 +365,11 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaFree(h->lane[0].d_ws), cudaFree(h->lane[1].d_ws);
     cudaFree(h->ro.contact), cudaFree(h->ro.phase_k), cudaFree(h->ro.t_swing), cudaFree(h->ro.controls);
     cudaFree(h->ro.tau), cudaFree(h->ro.status), cudaFree(h->ro.iters), cudaFree(h->ro.ws_mask);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->fork) cudaEventDestroy(h->fork);
+    if (h->join) cudaEventDestroy(h->join);
+    if (h->side) cudaStreamDestroy(h->side);
     delete h;
     return 0;
 }
@@ -524,16 +556,16 @@ int bmpc_enable_timing(bmpc_handle* h, int enable) {
     if (!h) return fail("bmpc_enable_timing: null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     if (enable && !h->ev[0])
-        for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+        for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     h->timing = enable ? 1 : 0;
     return 0;
 }
 
-int bmpc_last_timing(bmpc_handle* h, float* ms3) {
-    if (!h || !ms3 || !h->ev[0]) return fail("bmpc_last_timing: timing was not enabled");
+int bmpc_last_timing(bmpc_handle* h, float* ms4) {
+    if (!h || !ms4 || !h->ev[0]) return fail("bmpc_last_timing: timing was not enabled");
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaEventSynchronize(h->ev[3]));
-    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms3[i], h->ev[i], h->ev[i + 1]));
+    CUDA_TRY(cudaEventSynchronize(h->ev[4]));
+    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], h->ev[i], h->ev[i + 1]));
     return 0;
 }
 

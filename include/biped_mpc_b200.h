@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BMPC_ABI_VERSION 1
+#define BMPC_ABI_VERSION 2
 
 /* Mirror of `class MPC` (MPC.py:22-32) + `class Biped` (MPC.py:34-48) + solver options. */
 typedef struct bmpc_params {
@@ -157,10 +157,12 @@ int bmpc_set_option(bmpc_handle* h, const char* name, int value);
 int64_t bmpc_launch_count(const bmpc_handle* h);
 
 /* Per-kernel device timing of the last bmpc_step/bmpc_solve (CUDA events on the launching
- * stream): ms3 = {classify, walking-class kernel (<= h stance foot-stages), standing-class
- * kernel}.  bmpc_last_timing blocks until the tick has finished. */
+ * stream): ms4 = {classify, lane-per-robot kernels (the two instance classes run concurrently; 0 when the
+ * batch is below their size gates), walking-class warp-per-robot kernel (<= h stance foot-stages; after a lane launch:
+ * only what that did not certify), standing-class warp-per-robot kernel}.  bmpc_last_timing blocks
+ * until the tick has finished. */
 int bmpc_enable_timing(bmpc_handle* h, int enable);
-int bmpc_last_timing(bmpc_handle* h, float* ms3);
+int bmpc_last_timing(bmpc_handle* h, float* ms4);
 
 /* Measured CUDA-core FMA peak of the device (roofline denominator): fp64 != 0 selects
  * double precision.  Runs a register-resident FMA chain on every SM; result in TFLOP/s. */

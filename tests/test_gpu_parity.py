@@ -37,7 +37,7 @@ def _solver(variant=0, max_batch=256, lane=None, **kw):
 def test_library_loaded_and_no_fallback(torch_cuda):
     from biped_mpc_py_b200 import _lib
     lib = _lib.load()
-    assert lib.bmpc_abi_version() == 1
+    assert lib.bmpc_abi_version() == 2
 
 
 def test_assembly_matches_model(torch_cuda, golden):

@@ -47,7 +47,7 @@ for cfg in cfgs:
     ts = np.array(ts).min(axis=0)
     st = np.bincount(out["status"].cpu().numpy(), minlength=4).tolist()
     it = out["iters"].cpu().numpy()
-    line = (f"warps/cta {warps} ctas/sm {ctas} sync {sync} prefetch {pref}: walking {ts[1]:.2f} ms standing {ts[2]:.2f} ms -> "
+    line = (f"warps/cta {warps} ctas/sm {ctas} sync {sync} prefetch {pref}: lane {ts[1]:.2f} ms warp-per-robot {ts[2]:.2f} + {ts[3]:.2f} ms -> "
             f"{n / (ts.sum() * 1e-3) / 1e6:.3f} M solves/s  status {st} iters {it.mean():.3f}")
     u = out["controls"].cpu().numpy()
     if ref is None:
