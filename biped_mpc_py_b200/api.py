@@ -99,9 +99,9 @@ class BatchedMPC:
         _lib.check(self._lib.bmpc_enable_timing(self._h, int(on)))
 
     def last_timing_ms(self):
-        """(classify, lane-per-robot kernel, walking-class warp-per-robot kernel, standing-class warp-per-robot kernel)
-        device times of the last tick in ms."""
-        ms = (ctypes.c_float * 4)()
+        """(classify, lane kernel walking class, lane kernel standing class, warp-per-robot walking, warp-per-robot standing)
+        device times of the last tick in ms; while timing is enabled the kernels of a tick run serially."""
+        ms = (ctypes.c_float * 5)()
         _lib.check(self._lib.bmpc_last_timing(self._h, ms))
         return [float(v) for v in ms]
 

@@ -92,7 +92,7 @@ struct bmpc_handle {
     int warm_enabled = 0;        // bmpc_warm_start: bmpc_step / bmpc_solve start from the previous call's active set
     int warm_valid = 0;          // the store holds the masks of a previous call
     int timing = 0;              // record CUDA events around each kernel of a tick
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // the two lane-per-robot class kernels run concurrently: the standing class on the caller's stream, the walking class on
     // this side stream, so that the classes share one tail instead of each paying its own
     cudaStream_t side = nullptr;
@@ -160,38 +160,34 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    // Each class is an independent chain:  [lane-per-robot kernel] -> collect what it did not certify -> warp-per-robot
+    // kernel (-> h = 30: dense re-solve of the rest).  Throughput batches run the two chains CONCURRENTLY - the standing
+    // class (twice the work per robot, usually the smaller class) on the caller's stream, the walking class on a side
+    // stream - so that the classes share one tail instead of each paying its own.  With timing enabled the kernels run
+    // one after the other, each bracketed by events, so that the per-kernel durations are not blurred by the overlap.
     const bool use_lane = n >= h->lane_min && !io.warm && (h->lane[0].fn || h->lane[1].fn);
-    if (use_lane) {
-        // throughput batches: one THREAD per robot first (32 robots share every instruction); robots it does not certify
-        // (status 1) are collected below and solved by the warp-per-robot kernels.  The standing class (twice the work per
-        // robot, usually the smaller class) is launched first; the walking class follows on the side stream and fills the SMs
-        // as the standing CTAs run out of slices.
-        const bool both = h->lane[0].fn && h->lane[1].fn;
-        if (both) {
-            if (!h->side) {
-                CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-                CUDA_TRY(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming));
-            }
-            CUDA_TRY(cudaEventRecord(h->fork, st));
-            CUDA_TRY(cudaStreamWaitEvent(h->side, h->fork, 0));
+    const bool concurrent = use_lane && !h->timing;
+    if (concurrent) {
+        if (!h->side) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming));
         }
-        for (int b = 1; b >= 0; --b) {
-            LaneVariant& lv = h->lane[b];
-            if (!lv.fn) continue;
-            if (!lv.d_ws) CUDA_TRY(cudaMalloc(&lv.d_ws, sizeof(double) * lv.ws_doubles));
-            cudaStream_t ls = (both && b == 0) ? h->side : st;
-            lv.fn<<<std::min(lv.grid, (n + lv.threads - 1) / lv.threads), lv.threads, lv.smem, ls>>>(
-                h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b, h->d_counts + 12 + b, lv.d_ws, lv.min_count);
-            h->launches += 1;
-        }
-        if (both) {
-            CUDA_TRY(cudaEventRecord(h->join, h->side));
-            CUDA_TRY(cudaStreamWaitEvent(st, h->join, 0));
-        }
+        CUDA_TRY(cudaEventRecord(h->fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(h->side, h->fork, 0));
     }
-    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2], st));
-    for (int b = 0; b < 2; ++b) {
+    auto lane_launch = [&](int b, cudaStream_t ls) -> int {
+        LaneVariant& lv = h->lane[b];
+        if (!use_lane || !lv.fn) return 0;
+        // one THREAD per robot (32 robots share every instruction); a class below its size gate is left alone (decided on
+        // the device: the kernel returns at once and collect_or_all_kernel passes the whole list on)
+        if (!lv.d_ws) CUDA_TRY(cudaMalloc(&lv.d_ws, sizeof(double) * lv.ws_doubles));
+        lv.fn<<<std::min(lv.grid, (n + lv.threads - 1) / lv.threads), lv.threads, lv.smem, ls>>>(
+            h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b, h->d_counts + 12 + b, lv.d_ws, lv.min_count);
+        h->launches += 1;
+        return 0;
+    };
+    auto warp_launch = [&](int b, cudaStream_t ls) -> int {
         // real-time use (N = 1 .. 8): every walking robot gets a whole 128-thread CTA (0.26 ms instead of 0.32 ms for one
         // robot end to end).  Same optimum, but reductions run in a different order, so results of batches <= 8 may
         // differ in the last bits from the throughput kernel.
@@ -202,24 +198,39 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         const int* cnt = h->d_counts + b;
         if (use_lane && h->lane[b].fn) {
             int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
-            collect_or_all_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b, h->lane[b].min_count);
+            collect_or_all_kernel<<<(n + 255) / 256, 256, 0, ls>>>(list, cnt, io.status, rlist, h->d_counts + 6 + b, h->lane[b].min_count);
             list = rlist, cnt = h->d_counts + 6 + b;
             h->launches += 1;
         }
-        v.fn<<<grid, v.threads, v.smem, st>>>(h->dp, io, list, cnt, v.d_scratch);
-        if (b == 1 && h->fallback.fn) {
-            // instances of EITHER class that the stage-wise kernels did not certify: dense re-solve (handles any S <= 2h)
-            const Variant& f = h->fallback;
-            for (int c = 0; c < 2; ++c)
-                collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_lists + (size_t)c * h->max_batch, h->d_counts + c, io.status,
-                                                                           h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2);
-            const int fgrid = (std::min(n, f.resident) + f.per_cta - 1) / f.per_cta;
-            f.fn<<<fgrid, f.threads, f.smem, st>>>(h->dp, io, h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2, f.d_scratch);
-            h->launches += 3;
-        }
-        if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[3 + b], st));
+        v.fn<<<grid, v.threads, v.smem, ls>>>(h->dp, io, list, cnt, v.d_scratch);
+        h->launches += 1;
+        return 0;
+    };
+    if (concurrent) {
+        if (lane_launch(1, st) || lane_launch(0, h->side) || warp_launch(1, st) || warp_launch(0, h->side)) return 1;
+        CUDA_TRY(cudaEventRecord(h->join, h->side));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->join, 0));
+    } else {
+        if (lane_launch(0, st)) return 1;
+        if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[2], st));
+        if (lane_launch(1, st)) return 1;
+        if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[3], st));
+        if (warp_launch(0, st)) return 1;
+        if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[4], st));
+        if (warp_launch(1, st)) return 1;
     }
-    h->launches += 3;
+    if (h->fallback.fn) {
+        // h = 30: instances of EITHER class that the stage-wise kernels did not certify: dense re-solve (handles any S <= 2h)
+        const Variant& f = h->fallback;
+        for (int c = 0; c < 2; ++c)
+            collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_lists + (size_t)c * h->max_batch, h->d_counts + c, io.status,
+                                                                       h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2);
+        const int fgrid = (std::min(n, f.resident) + f.per_cta - 1) / f.per_cta;
+        f.fn<<<fgrid, f.threads, f.smem, st>>>(h->dp, io, h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2, f.d_scratch);
+        h->launches += 3;
+    }
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[5], st));
+    h->launches += 1;  // classify
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -243,9 +254,11 @@ int setup_lanes(bmpc_handle* h) {
     const int warps = h->opt_lane_warps > 0 ? h->opt_lane_warps : 4;
     const int ctas = h->opt_lane_ctas_per_sm > 0 ? h->opt_lane_ctas_per_sm : 0;
     const bool h30 = d.h == 30;
-    h->lane_min = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 6144 : 20480);
-    h->lane[0].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 12288 : 49152);
-    h->lane[1].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 6144 : 20480);
+    // measured crossovers against the warp-per-robot kernels (tools/gate_probe.py, profiles/r2_summary.md): h = 10 walking
+    // class ~8 k robots (3.8 vs 3.6 ms), standing ~4 k (6.2 vs 6.2 ms); h = 30 walking ~2 k (17 vs 18 ms), standing ~1 k (40 vs 45 ms)
+    h->lane_min = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 1024 : 4096);
+    h->lane[0].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 2048 : 8192);
+    h->lane[1].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 1024 : 4096);
     int rc = setup_lane(h->lane[0], d, 1, h->num_sms, ctas, warps, h->max_batch);
     if (!rc && mode >= 2) {
         const int mc = h->lane[1].min_count;
@@ -365,7 +378,7 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaFree(h->lane[0].d_ws), cudaFree(h->lane[1].d_ws);
     cudaFree(h->ro.contact), cudaFree(h->ro.phase_k), cudaFree(h->ro.t_swing), cudaFree(h->ro.controls);
     cudaFree(h->ro.tau), cudaFree(h->ro.status), cudaFree(h->ro.iters), cudaFree(h->ro.ws_mask);
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 6; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->fork) cudaEventDestroy(h->fork);
     if (h->join) cudaEventDestroy(h->join);
@@ -556,16 +569,16 @@ int bmpc_enable_timing(bmpc_handle* h, int enable) {
     if (!h) return fail("bmpc_enable_timing: null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     if (enable && !h->ev[0])
-        for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+        for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     h->timing = enable ? 1 : 0;
     return 0;
 }
 
-int bmpc_last_timing(bmpc_handle* h, float* ms4) {
-    if (!h || !ms4 || !h->ev[0]) return fail("bmpc_last_timing: timing was not enabled");
+int bmpc_last_timing(bmpc_handle* h, float* ms5) {
+    if (!h || !ms5 || !h->ev[0]) return fail("bmpc_last_timing: timing was not enabled");
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaEventSynchronize(h->ev[4]));
-    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], h->ev[i], h->ev[i + 1]));
+    CUDA_TRY(cudaEventSynchronize(h->ev[5]));
+    for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]));
     return 0;
 }
 

@@ -157,12 +157,14 @@ int bmpc_set_option(bmpc_handle* h, const char* name, int value);
 int64_t bmpc_launch_count(const bmpc_handle* h);
 
 /* Per-kernel device timing of the last bmpc_step/bmpc_solve (CUDA events on the launching
- * stream): ms4 = {classify, lane-per-robot kernels (the two instance classes run concurrently; 0 when the
- * batch is below their size gates), walking-class warp-per-robot kernel (<= h stance foot-stages; after a lane launch:
- * only what that did not certify), standing-class warp-per-robot kernel}.  bmpc_last_timing blocks
- * until the tick has finished. */
+ * stream): ms5 = {classify, lane-per-robot kernel of the walking class, lane-per-robot kernel of the
+ * standing class (each 0 when the batch is below the size gates), walking-class warp-per-robot kernel
+ * (<= h stance foot-stages; after a lane launch: the collect step + what that did not certify),
+ * standing-class warp-per-robot kernel (+ the h = 30 dense re-solve)}.  While timing is enabled the
+ * kernels of a tick run one after the other (normally the two classes run concurrently on two
+ * streams), so the five intervals do not overlap.  bmpc_last_timing blocks until the tick has finished. */
 int bmpc_enable_timing(bmpc_handle* h, int enable);
-int bmpc_last_timing(bmpc_handle* h, float* ms4);
+int bmpc_last_timing(bmpc_handle* h, float* ms5);
 
 /* Measured CUDA-core FMA peak of the device (roofline denominator): fp64 != 0 selects
  * double precision.  Runs a register-resident FMA chain on every SM; result in TFLOP/s. */

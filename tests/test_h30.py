@@ -43,20 +43,34 @@ def test_h30_known_answer_g5_and_random_instances():
     s.close()
 
 
-def test_h30_batch_all_certified_and_split_invariant():
-    """4,096 horizon-30 instances: every one certified optimal; results do not depend on the batch split."""
+@pytest.mark.parametrize("family", ["lane", "warp", "default"])
+def test_h30_batch_all_certified_and_split_invariant(family):
+    """4,096 horizon-30 instances: every one certified optimal.  With the kernel family pinned (lane-per-robot kernels for every
+    class, or warp-per-robot kernels only) results do not depend on the batch split, bit for bit; under the default dispatch
+    the size gates may hand a class of the half batch to the other family, which reaches the same certified optimum
+    with different rounding (include/biped_mpc_b200.h, "sharding")."""
     import torch
     from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
     mpc = MPC(h=30)
     n = 4096
     b = synth.make_batch(n, shard_index=12, mpc=mpc, extend=True)
     s = BatchedMPC(mpc, Biped(), max_batch=n, extend_gait=True)
+    if family == "lane":
+        s.set_option("lane_min", 1)
+    elif family == "warp":
+        s.set_option("lane_mode", 0)
     args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
     full = s.step_host(*args, phase_k=b["phase_k"])
     assert (full["status"] == 0).all(), np.bincount(full["status"], minlength=4)
     half = s.step_host(*[a[:n // 2] for a in args], phase_k=b["phase_k"][:n // 2])
-    np.testing.assert_array_equal(half["controls"], full["controls"][:n // 2])
-    np.testing.assert_array_equal(half["tau"], full["tau"][:n // 2])
+    if family == "default":
+        scale = np.maximum(1.0, np.abs(full["controls"][:n // 2]).reshape(n // 2, -1).max(axis=1))
+        du = np.abs(half["controls"] - full["controls"][:n // 2]).reshape(n // 2, -1).max(axis=1) / scale
+        assert du.max() <= 1e-6, du.max()
+        assert np.abs(half["tau"] - full["tau"][:n // 2]).max() <= 1e-6
+    else:
+        np.testing.assert_array_equal(half["controls"], full["controls"][:n // 2])
+        np.testing.assert_array_equal(half["tau"], full["tau"][:n // 2])
     s.close()
 
 

@@ -23,6 +23,6 @@ for _ in range(3):
 ts = np.array(ts).mean(axis=0)
 st = np.bincount(out["status"].cpu().numpy(), minlength=4).tolist()
 it = out["iters"].cpu().numpy()
-print(json.dumps(dict(h=30, n=n, walking=int(b["gait"].sum()), standing=int(n - b["gait"].sum()), lane_ms=float(ts[1]),
-                      warp_walking_ms=float(ts[2]), warp_standing_ms=float(ts[3]), solves_per_s=n / (ts.sum() * 1e-3), status=st, mean_iters=float(it.mean()),
+print(json.dumps(dict(h=30, n=n, walking=int(b["gait"].sum()), standing=int(n - b["gait"].sum()), lane_walking_ms=float(ts[1]), lane_standing_ms=float(ts[2]),
+                      warp_walking_ms=float(ts[3]), warp_standing_ms=float(ts[4]), solves_per_s=n / (ts.sum() * 1e-3), status=st, mean_iters=float(it.mean()),
                       max_iters=int(it.max()))))

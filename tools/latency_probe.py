@@ -23,7 +23,7 @@ for gait_sel in (1, 0):
         t1.run(); ks.append(one.last_timing_ms())
     ks = np.median(np.array(ks), axis=0)
     print(f"gait={gait_sel} p50 {np.percentile(lat,50):.3f} ms p99 {np.percentile(lat,99):.3f} ms | device: classify {ks[0]*1e3:.1f} us, "
-          f"walking kernel {ks[2]*1e3:.1f} us, standing kernel {ks[3]*1e3:.1f} us | iters {int(t1.outputs['iters'][0])}")
+          f"walking kernel {ks[3]*1e3:.1f} us, standing kernel {ks[4]*1e3:.1f} us | iters {int(t1.outputs['iters'][0])}")
     one.close()
 
 

@@ -25,5 +25,5 @@ for _ in range(4):
 ts = np.array(ts).mean(axis=0)
 st = np.bincount(out["status"].cpu().numpy(), minlength=4).tolist()
 print(f"mu_tol={mu_tol} rd_tol={rd_tol} n={n} NWW={os.environ.get('BMPC_NW_WALK','8')} NTS={os.environ.get('BMPC_NT_STAND','128')} "
-      f"lane {ts[1]:.2f} warp-walk {ts[2]:.2f} warp-stand {ts[3]:.2f} ms -> {n/(ts.sum()*1e-3)/1e6:.3f} M solves/s  status {st} "
+      f"lane {ts[1]:.2f} + {ts[2]:.2f} warp-per-robot {ts[3]:.2f} + {ts[4]:.2f} ms -> {n/(ts.sum()*1e-3)/1e6:.3f} M solves/s  status {st} "
       f"iters {float(out['iters'].float().mean()):.3f}")
