@@ -17,16 +17,26 @@ import os
 
 for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")  # the CPU legs run one process per core
-if not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
-    # NCCL prints its version banner on STDOUT at VERSION level and above (the level can also come from
-    # /etc/nccl.conf); rank 0 must print exactly one JSON line, so debug output goes to stderr's file instead
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL writes its debug output (communicator ranks, rings, NVLS) to STDOUT.  Rank 0 must print exactly one JSON line
+# there, so the process's fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved stdout:
+# NCCL_DEBUG=INFO stays visible (on stderr) for whoever wants to check the communicator.
+os.environ.setdefault("NCCL_DEBUG", "INFO")
+os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
 
 import argparse
 import json
 import sys
 import threading
 import time
+
+sys.stdout.flush()
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 import numpy as np
 
@@ -82,27 +92,28 @@ def flops_per_solve(S, iters, LB=5, mb=11, h=10, stages=None, polish_rounds=1.15
 
 
 def flops_per_solve_lane(S, iters, LB=5, mb=11, h=10, polish_rounds=1.15):
-    """Restated for the stage-wise (Riccati) factorisation of the lane-per-robot kernel (SURVEY.md 8d asks for that when
-    the factorisation differs): per stage with one stance foot the sweep is 1,211 FMA (P B 360, G + Cholesky
-    125, F column operation 60, Y = inv(L) F 120, congruence 156, rank-5 update 390), a solve 224 FMA (backward + forward);
-    one iteration = one sweep + two solves (no Gondzio corrector in this kernel) + the row passes + the stage weights."""
+    """Restated for the stage-wise (Riccati) factorisation of the lane-per-robot kernels (SURVEY.md 8d asks for that when the
+    factorisation differs).  Per virtual stage (one block of 5 inputs, structural input map):
+    factor 1,176 FMA (P B 216, G 51, Cholesky 30, backward half of the solve 33 + 70, Yt = inv(L)(P B)' 180, rank-5 downdate
+    of the cost-to-go 390, Y = Yt A 50, congruence A'PA 156); the other backward half 103 FMA, a forward half 103 FMA.
+    One iteration = one factor sweep + three more half solves + the row work (priced with the dense count of the
+    warp-per-robot model so that the two kernel families are comparable: the recomputation the lane kernel does instead of
+    storing row quantities is NOT counted)."""
     m = mb * S
-    per_foot = S / float(h)
-    f_sweep, f_solve, f_grad = 2.0 * 1211.0 * h * per_foot, 2.0 * 224.0 * h * per_foot, 2.0 * 120.0 * h * per_foot
-    f_setup = 250.0 * h + 40.0 * S * h + f_grad
-    f_iter = f_sweep + 2.0 * f_solve + m * (8.0 * LB + 20.0) + S * mb * LB * (LB + 1.0)
-    f_polish = f_sweep + f_solve + 3.0 * f_grad + 4.0 * LB ** 3 * S
+    f_factor, f_half, f_grad = 2.0 * 1176.0 * S, 2.0 * 103.0 * S, 2.0 * 120.0 * S
+    f_setup = 250.0 * h + 40.0 * S * h + 2.0 * f_grad
+    f_iter = f_factor + 3.0 * f_half + m * (8.0 * LB + 20.0) + S * mb * LB * (LB + 1.0)
+    f_polish = f_factor + f_half + 2.0 * f_grad + 2.0 * (2.0 * 275.0 + 300.0) * S + 4.0 * LB ** 3 * S
     return f_setup + iters * f_iter + (polish_rounds * f_polish if S > 0 else 0.0) + 600.0
 
 
+LANE_GATES = {10: (4096, 8192, 4096), 30: (1024, 2048, 1024)}  # batch, walking class, standing class (bmpc.cu::setup_lanes)
+
+
 def lane_front_end_active(n, class_count, cls, h=10):
-    """Mirror of the size gates in bmpc.cu / lane_tick_kernel: the lane-per-robot kernel takes a class only when the batch has
-    >= 20,480 robots and the class >= 49,152 (walking) / 20,480 (standing) robots; BMPC_LANE_MIN overrides all three."""
-    mode = os.environ.get("BMPC_LANE", "2")
-    if h != 10 or mode == "0" or (cls == 1 and mode == "1"):
-        return False
-    ov = os.environ.get("BMPC_LANE_MIN")
-    n_min, c_min = (int(ov), int(ov)) if ov else (20480, (49152, 20480)[cls])
+    """Mirror of the size gates in bmpc.cu / lane_tick_kernel: the lane-per-robot kernel takes a class only when the batch
+    and the class are above the measured crossover against the warp-per-robot kernels."""
+    n_min, c_min = LANE_GATES[h][0], LANE_GATES[h][1 + cls]
     return n >= n_min and class_count >= c_min
 
 
@@ -116,7 +127,8 @@ def batch_flops(contact, iters, lane=False, lane_both=False):
         sel = (per_stage == feet).all(axis=1)
         base = flops_per_solve_lane(feet * h, 0.0, h=h)
         per_it = flops_per_solve_lane(feet * h, 1.0, h=h) - base
-        total[cls] += sel.sum() * base + float(iters[sel].sum()) * per_it
+        # (the reported iteration count includes the last one, which only tests convergence and factors nothing)
+        total[cls] += sel.sum() * base + float(np.maximum(iters[sel] - 1, 0).sum()) * per_it
         contact, iters, S, per_stage = contact[~sel], iters[~sel], S[~sel], per_stage[~sel]
     for s_val in np.unique(S):
         sel = S == s_val
@@ -175,28 +187,40 @@ def cpu_leg(per_core):
                       f"reference dense assembly + dense full-size interior point at cvxopt default tolerances "
                       f"(cvxopt-class stand-in; the real cvxopt is not installable) + lowLevelControl; "
                       f"{r['ms_per_solve']:.1f} ms per solve per core, of which assembly {r['ms_assembly']:.1f} ms",
-            "per_core_value": r["per_core_solves_per_s"]}
+            "per_core_value": r["per_core_solves_per_s"], "solves": r["solves"]}
+
+
+REF_PER_CORE_PER_STEP = 128  # x (warmup + steps) >= 1,000 solves per process for the default --steps 10 --warmup 3
 
 
 def run_reference(args, rank):
+    """CPU arm: the oracle port (kind "port": reference-semantics dense assembly + dense interior point at cvxopt-default
+    tolerances + lowLevelControl; cvxopt itself is not installable here) on every host core.  A step is a bounded sample of the
+    workload: REF_PER_CORE_PER_STEP ticks per core."""
     if rank != 0:
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_leg(per_core=8)
+        r = cpu_leg(per_core=REF_PER_CORE_PER_STEP)
         if i >= args.warmup:
             vals.append(r)
     value = float(np.mean([v["value"] for v in vals]))
     cores = vals[-1]["cores"]
-    n_per_step = 8 * cores
+    n_per_step = REF_PER_CORE_PER_STEP * cores
+    cfg = workload_config(args.batch, args.gpus)
+    cfg["workload"] = (f"CPU arm: {n_per_step} horizon-10 biped MPC ticks per step ({REF_PER_CORE_PER_STEP} per core on {cores} host cores) drawn "
+                       f"from the same synthetic distribution as the GPU arm's {args.batch}-instance batch (BASELINE.json configs[2]; 85% walking / "
+                       "15% standing, SURVEY.md 8d) - a bounded sample of that workload, not the whole batch")
+    cfg["instances_per_step"] = n_per_step
+    cfg["solves_per_process"] = REF_PER_CORE_PER_STEP * (args.warmup + args.steps)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_per_step / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.batch, args.gpus),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -219,13 +243,13 @@ def other_configs(torch, dev, local_rank, rank, world, barrier, max_over_ranks, 
         return max_over_ranks(e0.elapsed_time(e1)) / reps, r
 
     # configs[3]: horizon 30 (periodic gait extension for the walking instances; standing is reference-defined)
-    n30 = 65536  # large enough for the lane-per-robot kernels (size gates 12,288 walking / 6,144 standing robots at h = 30)
+    n30 = 65536
     mpc30 = MPC(h=30)
     b = synth.make_batch(n30, shard_index=1000 + rank, mpc=mpc30, extend=True)
     s30 = BatchedMPC(mpc30, Biped(), max_batch=n30, device=local_rank, extend_gait=True)
     d = [tn(b["x_fb"]), tn(b["phase_k"], torch.int32), tn(b["t"]), tn(b["foot"]), tn(b["contact"], torch.uint8),
          tn(b["q"]), tn(b["qd"]), tn(b["pf_w"])]
-    ms, r = timed(lambda: s30.step(*d), 2)
+    ms, r = timed(lambda: s30.step(*d), 5)
     st = r["status"].cpu().numpy()
     out["h30"] = {"workload": f"{n30} horizon-30 ticks per GPU (BASELINE.json configs[3]; 85% walking with the periodic gait "
                               "extension, 15% standing)", "solves_per_s": world * n30 / (ms * 1e-3), "ms_per_step": ms,
@@ -234,17 +258,25 @@ def other_configs(torch, dev, local_rank, rank, world, barrier, max_over_ranks, 
     s30.close()
 
     # configs[4]: closed-loop rollout (MPC + J^T torques + SRB plant, rules R1-R7 of DESIGN.md 9)
-    nr, ticks = 16384, 100
+    nr, ticks = 16384, 1000
     sr = BatchedMPC(MPC(), synth.rollout_biped(), max_batch=nr, device=local_rank)
     rb = synth.make_rollout_batch(nr, shard_index=rank)
     for mode, warm in (("warm", True), ("cold", False)):
-        def run():
+        def short():
             stt = [tn(rb["x"]), tn(rb["foot"]), tn(rb["tick"], torch.int32), tn(rb["gait"], torch.uint8), tn(rb["q"]), tn(rb["qd"])]
-            return sr.rollout(*stt, ticks, warm_start=warm)
-        ms, r = timed(run, 1)
+            return sr.rollout(*stt, 10, warm_start=warm)
+        short()  # warm-up: allocations, first launches
+        stt = [tn(rb["x"]), tn(rb["foot"]), tn(rb["tick"], torch.int32), tn(rb["gait"], torch.uint8), tn(rb["q"]), tn(rb["qd"])]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = sr.rollout(*stt, ticks, warm_start=warm)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
         sn = BatchedMPC.rollout_stats(r["stats"])
-        out["rollout_" + mode] = {"workload": f"{nr} robots x {ticks} ticks per GPU, closed loop (BASELINE.json configs[4] at a "
-                                              f"tenth of its 1,000 ticks), warm_start={warm}; includes the H2D of the initial states",
+        out["rollout_" + mode] = {"workload": f"{nr} robots x {ticks} ticks per GPU, closed loop (BASELINE.json configs[4]), "
+                                              f"warm_start={warm}; initial states resident on the device",
                                   "robot_ticks_per_s": world * nr * ticks / (ms * 1e-3), "ms_per_tick": ms / ticks,
                                   "mean_iters": sn["mean_iters"], "warm_hit_rate": sn["warm_hit_rate"],
                                   "not_optimal": int(sum_over_ranks(float(sn["not_optimal"]))),
@@ -266,20 +298,10 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its version banner to STDOUT when the communicator is created; rank 0 must print exactly one
-        # JSON line, so file descriptor 1 points at stderr while the communicator comes up
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)
-            torch.cuda.synchronize(dev)
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        torch.cuda.synchronize(dev)
 
     def barrier():
         if world > 1:
@@ -338,86 +360,113 @@ def run_b200(args, rank, local_rank, world):
     status = out["status"].cpu().numpy()
     resid = out["resid"].cpu().numpy()
 
-    # ---- roofline of the two solve kernels (events inside the C ABI, same stream) ---------
+    # ---- roofline of the solve kernels (events inside the C ABI, same stream; with timing on, the kernels of a tick run
+    #      one after the other so that the five intervals do not overlap) ----------------------------------------------
     solver.enable_timing(True)
     kt = []
     for _ in range(max(3, min(args.steps, 10))):
         step()
         kt.append(solver.last_timing_ms())
     solver.enable_timing(False)
-    kt = np.array(kt).mean(axis=0)  # classify, walking-class, standing-class
+    kt = np.array(kt).mean(axis=0)  # classify, lane walking, lane standing, warp-per-robot walking, warp-per-robot standing
     cls_count = np.bincount((batch["contact"].reshape(n, -1).sum(axis=1) > 10).astype(int), minlength=2)
     lane = lane_front_end_active(n, int(cls_count[0]), 0)
     lane_both = lane and lane_front_end_active(n, int(cls_count[1]), 1)
     fl = batch_flops(batch["contact"], iters, lane=lane, lane_both=lane_both)
     fl_dense = batch_flops(batch["contact"], iters)
     peaks = measure(local_rank)
+    names = {("lane", 0): "lane_tick_kernel<10,1,RM> (walking class: one THREAD per robot, stage-wise Riccati sweeps, bmpc_lane.cuh)",
+             ("lane", 1): "lane_tick_kernel<10,2,RM> (standing class: one THREAD per robot, two virtual stages of one 5-input block per stage)",
+             ("warp", 0): "mpc_tick2_kernel<10,10,5,32,8> (walking class, one warp per robot, 8 robots per CTA; after a lane launch: collect + "
+                          "what the lane kernel did not certify)",
+             ("warp", 1): "mpc_tick2_kernel<10,20,5,128,1> (standing class, one CTA per robot; after a lane launch: collect + the rest)"}
     kernels = []
-    walk_name = ("lane_tick_kernel<10,1,5> (walking class: one THREAD per robot, stage-wise Riccati sweep; + collect + "
-                 "mpc_tick2_kernel<10,10,5,32,8> for what it does not certify)") if lane else \
-        "mpc_tick2_kernel<10,10,5,32,8> (<=10 stance foot-stages: walking class, one warp per robot, 8 robots per CTA)"
-    stand_name = ("lane_tick_kernel<10,2,5> (standing class: one THREAD per robot, two virtual stages of one 5-input block per stage; "
-                  "+ collect + mpc_tick2_kernel<10,20,5,128,1> for what it does not certify)") if lane_both else \
-        "mpc_tick2_kernel<10,20,5,128,1> (11..20 stance foot-stages: standing class, one CTA per robot)"
-    for cls, name in ((0, walk_name), (1, stand_name)):
-        ach = fl[cls] / (kt[1 + cls] * 1e-3) / 1e12 if kt[1 + cls] > 0 else 0.0
-        kernels.append({"kernel": name, "ms_per_launch": float(kt[1 + cls]), "algorithmic_gflop_per_launch": fl[cls] / 1e9,
-                        "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"],
+    for cls, is_lane in ((0, lane), (1, lane_both)):
+        ms = float(kt[1 + cls]) if is_lane else float(kt[3 + cls])
+        ach = fl[cls] / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        kernels.append({"kernel": names[("lane" if is_lane else "warp", cls)], "ms_per_launch": ms,
+                        "algorithmic_gflop_per_launch": fl[cls] / 1e9, "achieved_tflops": ach, "frac": ach / peaks["fp64_fma_tflops"],
+                        "fall_through_ms": float(kt[3 + cls]) if is_lane else None,
                         # the same launch priced with the DENSE condensed-form count of the warp-per-robot kernels: the
                         # stage-wise form needs 1.7x (walking) / 5x (standing) fewer FLOPs for the same solves
-                        "frac_at_dense_flop_count": (fl_dense[cls] / (kt[1 + cls] * 1e-3) / 1e12 / peaks["fp64_fma_tflops"]) if kt[1 + cls] > 0 else 0.0})
-    dom = int(np.argmax(kt[1:]))
+                        "frac_at_dense_flop_count": (fl_dense[cls] / (ms * 1e-3) / 1e12 / peaks["fp64_fma_tflops"]) if ms > 0 else 0.0})
+    dom = int(np.argmax([k["ms_per_launch"] for k in kernels]))
     traffic, secondary = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from one ncu capture of this batch size
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if int(tj.get("batch", -1)) == n:
-            traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
-        kd = tj["kernels"][dom]
-        if "smem_wavefronts_pct_of_peak" in kd:  # the nearest hardware limit per ncu (not measured live: profiler-only counters)
-            secondary = {"what": "pipe utilisation of the dominant kernel from the committed ncu capture",
-                         "smem_wavefronts_pct_of_peak": kd["smem_wavefronts_pct_of_peak"],
-                         "fp64_pipe_pct_busy": kd["fp64_pipe_pct_busy"], "issue_slots_pct_busy": kd["issue_slots_pct_busy"],
-                         "gcc_instruction_cache_busy_pct": kd.get("gcc_instruction_cache_busy_pct"),
-                         "source": tj.get("pipe_source")}
+        tk = tj.get("kernels", {})
+        kd = tk.get(("lane_" if (lane, lane_both)[dom] else "warp_") + ("walking", "standing")[dom]) if isinstance(tk, dict) else None
+        if kd:
+            if int(tj.get("batch", -1)) == n:
+                traffic = kd["dram_bytes_per_launch"]
+            secondary = {"what": "pipe utilisation of the dominant kernel from the committed ncu capture (profiler-only counters, not measured live)",
+                         "fp64_pipe_pct_busy": kd.get("fp64_pipe_pct_busy"), "issue_slots_pct_busy": kd.get("issue_slots_pct_busy"),
+                         "threads_per_instruction": kd.get("threads_per_instruction"),
+                         "l2_hit_rate_pct": kd.get("l2_hit_rate_pct"), "source": tj.get("source")}
+    ksum = float(kt.sum())
     roofline = {"bound": "fp64_fma", "achieved": kernels[dom]["achieved_tflops"], "peak": peaks["fp64_fma_tflops"],
                 "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": traffic,
                 "peak_source": "measured in this run by bmpc_measure_fma_peak (register-resident DFMA chains on all SMs); "
                                "MEASURED_PEAKS.json carries no FP64 CUDA-core figure",
                 "fp32_fma_peak_tflops": peaks["fp32_fma_tflops"], "dominant_kernel": kernels[dom]["kernel"],
                 "kernels": kernels, "classify_ms": float(kt[0]),
-                "share_of_step": {"walking": float(kt[1] / kt.sum()), "standing": float(kt[2] / kt.sum())},
+                "serial_ms": {"classify": float(kt[0]), "lane_walking": float(kt[1]), "lane_standing": float(kt[2]),
+                              "warp_walking": float(kt[3]), "warp_standing": float(kt[4]), "sum": ksum,
+                              "note": "per-kernel durations with the kernels of a tick run one after the other; in the timed region the two "
+                                      "class chains run concurrently on two streams, so ms_per_step is below this sum"},
+                "share_of_step": {"lane_walking": float(kt[1] / ksum), "lane_standing": float(kt[2] / ksum),
+                                  "warp_walking": float(kt[3] / ksum), "warp_standing": float(kt[4] / ksum)},
+                "whole_step_frac": float(sum(fl.values()) / (ms_per_step * 1e-3) / 1e12 / peaks["fp64_fma_tflops"]),
                 "secondary": secondary}
     if traffic is not None and kernels[dom]["ms_per_launch"] > 0:
-        # the lane-per-robot kernel streams its per-robot work arrays through DRAM: report that against the measured copy bandwidth
+        # the lane-per-robot kernels stream their per-robot block records through L2 / DRAM: report that against the measured copy bandwidth
         hbm_peak = 6543.1
         try:
             hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
         except Exception:
             pass
         gbs = traffic / 1e9 / (kernels[dom]["ms_per_launch"] * 1e-3)
-        roofline["hbm_view"] = {"what": "measured DRAM bytes of the dominant kernel (ncu, profiles/traffic.json) / its live duration: work-array "
+        roofline["hbm_view"] = {"what": "measured DRAM bytes of the dominant kernel (ncu, profiles/traffic.json) / its live duration: block-record "
                                         "streaming, not algorithmic bytes (~1.5 KB per robot)",
                                 "dram_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak,
-                                "dram_bytes_per_robot": traffic / max(1, int((batch["contact"].reshape(n, -1, 2).sum(axis=2) == 1).all(axis=1).sum()))
-                                if lane else None}
+                                "dram_bytes_per_robot": traffic / max(1, int(cls_count[dom]))}
 
-    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------
-    tick = solver.pinned_tick(n, lowlevel=True, want_states=False)
-    for k in ("x_fb", "foot", "q", "qd", "pf_w", "t", "phase_k", "contact"):
-        tick.inputs[k][...] = batch[k]
-    for _ in range(args.warmup):
-        tick.run()
+    # ---- e2e: host buffers through the public API, H2D + D2H of every step inside the timed region -----------------
+    # Two ticks (slots) of two chunks each: step i+1 is launched before the host reads the result of step i, so the copies of
+    # one step run under the kernels of the other (BatchedMPC.chunked_tick, api.py).  Every step copies its packed inputs from
+    # pinned host memory and its packed results back to pinned host memory, one cudaMemcpyAsync per chunk and direction.
+    keys = ("x_fb", "foot", "q", "qd", "pf_w", "t", "phase_k", "contact")
+    n_chunks = 2 if n >= 2 * 16384 else 1
+    ticks = [solver.chunked_tick(n, n_chunks, lowlevel=True, want_states=False, slot=k) for k in range(2)]
+    for tk in ticks:
+        tk.set_inputs(**{k: batch[k] for k in keys})
+    for _ in range(max(1, args.warmup)):
+        for tk in ticks:
+            tk.run()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = tick.run()
-        _ = float(res["tau"][0, 0])  # host read of the step's result
+    ticks[0].launch()
+    for i in range(1, args.steps):
+        ticks[i % 2].launch()
+        res = ticks[(i - 1) % 2].wait()
+        _ = float(res[0]["tau"][0, 0])  # host read of the step's result
+    res = ticks[(args.steps - 1) % 2].wait()
+    _ = float(res[0]["tau"][0, 0])
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": total_n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tick.h2d_bytes),
-           "d2h_bytes_per_step": int(tick.d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
-           "api": "BatchedMPC.pinned_tick(n).run(): pinned host -> device, bmpc_step, device -> pinned host, sync"}
+    # the same through ONE synchronous call per step (no overlap between steps)
+    t0 = time.perf_counter()
+    for _ in range(min(args.steps, 5)):
+        res = ticks[0].run()
+        _ = float(res[0]["tau"][0, 0])
+    sync_s = max_over_ranks(time.perf_counter() - t0) / min(args.steps, 5)
+    e2e = {"value": total_n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(ticks[0].h2d_bytes),
+           "d2h_bytes_per_step": int(ticks[0].d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": f"BatchedMPC.chunked_tick(n, chunks={n_chunks}, slot=0|1): launch() of step i+1 before wait() of step i; per chunk one "
+                  "cudaMemcpyAsync pinned host -> device, bmpc_step, one cudaMemcpyAsync device -> pinned host",
+           "synchronous_single_call": {"value": total_n / sync_s, "ms_per_step": 1e3 * sync_s,
+                                       "api": f"chunked_tick(n, chunks={n_chunks}).run(): copies in, kernels, copies out, wait - one step at a time"}}
 
     # ---- stats reduction (the only collective): NCCL sum / max over ranks --------------------
     from biped_mpc_py_b200.shard import local_stats, reduce_stats
@@ -476,7 +525,7 @@ def run_b200(args, rank, local_rank, world):
             loop.close()
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cpu = cpu_leg(per_core=12)
+            cpu = cpu_leg(per_core=1000)  # >= 1,000 solves per process: ~20 s on every host core
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world, args.scaling),
@@ -486,7 +535,7 @@ def run_b200(args, rank, local_rank, world):
                            "not_optimal": int(stats["not_optimal"]), "bad_input": int(stats["bad_input"]),
                            "max_mu": float(stats["mu_max"]), "max_rd": float(stats["rd_max"]),
                            "instances": int(stats["instances"])}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     solver.close()
     if world > 1:
         dist.barrier()

@@ -64,9 +64,17 @@ class BatchedMPC:
         self.fric_active = torch.empty((nb, h), dtype=torch.uint8, device=dev)
         self.resid = torch.empty((nb, 2), dtype=f64, device=dev)
         self._stage = None  # packed host/device staging, created on first *_host call
+        self._ctor = dict(max_iter=max_iter, mu_tol=mu_tol, rd_tol=rd_tol)
+        self._options: Dict[str, int] = {}
+        self._children: list = []       # per-chunk handles of the chunked host path (ChunkedTick)
+        self._warm = None
+        self.host_chunk = 65536         # robots per chunk of the chunked host path (step_host for batches of two chunks or more)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
+        for c in getattr(self, "_children", []):
+            c.close()
+        self._children = []
         if getattr(self, "_h", None):
             self._lib.bmpc_destroy(self._h)
             self._h = None
@@ -85,11 +93,15 @@ class BatchedMPC:
         """Dispatch tunables of include/biped_mpc_b200.h::bmpc_set_option (``lane_mode``, ``lane_min``,
         ``lane_ctas_per_sm``, ``lane_warps``, ``lowlat``); every setting returns the same certified optimum."""
         _lib.check(self._lib.bmpc_set_option(self._h, name.encode(), int(value)))
+        self._options[name] = int(value)
+        for c in self._children:
+            c.set_option(name, value)
 
     def warm_start(self, on: bool = True):
         """Warm start across consecutive ``step`` / ``solve`` calls of a caller-owned control loop: robot i of the
         batch must be the same robot one tick later.  Same certified optimum as the cold solve, ~3x faster ticks."""
         _lib.check(self._lib.bmpc_warm_start(self._h, 1 if on else 0))
+        self._warm = bool(on)  # (the chunked host path is not used with warm start: the active sets live in this handle)
 
     def reset_warm_start(self):
         """Forget the stored active sets (after a state reset or a jump in time); warm start stays enabled."""
@@ -273,6 +285,36 @@ class BatchedMPC:
         """Zero-copy host interface: numpy views into pinned staging to fill, then ``run()``."""
         return PinnedTick(self, n, lowlevel, want_states)
 
+    def chunked_tick(self, n: int, chunks: int = 0, lowlevel: bool = True, want_states: bool = False, slot: int = 0) -> "ChunkedTick":
+        """Host interface for throughput batches: the batch is cut into ``chunks`` pieces (default: ``host_chunk`` robots each),
+        each with its own handle, CUDA stream and packed pinned staging, so that the host->device copy of chunk k+1 and the
+        device->host copy of chunk k-1 run under the kernels of chunk k.  Ticks with different ``slot`` numbers own disjoint
+        handles and staging: ``launch()`` slot 1 before ``wait()``-ing for slot 0 to pipeline consecutive steps (the copies of
+        one step then run under the kernels of the other)."""
+        if chunks <= 0:
+            chunks = max(1, n // self.host_chunk)
+        return ChunkedTick(self, n, chunks, lowlevel, want_states, slot)
+
+    def _chunk_solvers(self, count: int, chunk_n: int, first: int = 0):
+        """Child handles ``first .. first+count-1`` for batches up to ``chunk_n`` (same parameters, device and options), each
+        with its own stream."""
+        torch = _torch()
+        if any(c.max_batch < chunk_n for c in self._children[first:first + count]):
+            self._children = self._drop_children()
+        while len(self._children) < first + count:
+            c = BatchedMPC(self.mpc, self.biped, max_batch=chunk_n, device=self.device_index, extend_gait=self.extend_gait,
+                           **self._ctor)
+            c._own_stream = torch.cuda.Stream(device=self.device)
+            for k, v in self._options.items():
+                c.set_option(k, v)
+            self._children.append(c)
+        return self._children[first:first + count]
+
+    def _drop_children(self):
+        for c in self._children:
+            c.close()
+        return []
+
     def step_host(self, x_fb, t, foot, contact, q, qd, pf_w, phase_k=None, want_states: bool = False,
                   lowlevel: bool = True):
         """End-to-end tick with HOST numpy inputs and outputs (one H2D and one D2H copy).
@@ -288,17 +330,22 @@ class BatchedMPC:
         if phase_k is None:
             period = 10 if self.extend_gait else h
             phase_k = (gait_phase(t, self.mpc) % period)
-        tick = self.pinned_tick(n, lowlevel, want_states)
-        ins = tick.inputs
-        ins["x_fb"][...] = x_fb
-        ins["foot"][...] = np.asarray(foot, dtype=np.float64).reshape(n, 6)
-        ins["phase_k"][...] = np.asarray(phase_k, dtype=np.int32).reshape(n)
-        ins["contact"][...] = np.asarray(contact, dtype=np.uint8).reshape(n, h, 2)
+        arrays = dict(x_fb=x_fb, foot=np.asarray(foot, dtype=np.float64).reshape(n, 6),
+                      phase_k=np.asarray(phase_k, dtype=np.int32).reshape(n),
+                      contact=np.asarray(contact, dtype=np.uint8).reshape(n, h, 2))
         if lowlevel:
-            ins["q"][...] = np.asarray(q, dtype=np.float64).reshape(n, 10)
-            ins["qd"][...] = np.asarray(qd, dtype=np.float64).reshape(n, 10)
-            ins["pf_w"][...] = np.asarray(pf_w, dtype=np.float64).reshape(n, 6)
-            ins["t"][...] = t
+            arrays.update(q=np.asarray(q, dtype=np.float64).reshape(n, 10), qd=np.asarray(qd, dtype=np.float64).reshape(n, 10),
+                          pf_w=np.asarray(pf_w, dtype=np.float64).reshape(n, 6), t=t)
+        if n >= 2 * self.host_chunk and not self._warm:
+            # throughput batch: chunked, copies overlapped with the kernels of the neighbouring chunks
+            tick = self.chunked_tick(n, 0, lowlevel, want_states)
+            tick.set_inputs(**arrays)
+            tick.run()
+            self.last_h2d_bytes, self.last_d2h_bytes = tick.h2d_bytes, tick.d2h_bytes
+            return tick.gather()
+        tick = self.pinned_tick(n, lowlevel, want_states)
+        for k, a in arrays.items():
+            tick.inputs[k][...] = a
         out = tick.run()
         self.last_h2d_bytes, self.last_d2h_bytes = tick.h2d_bytes, tick.d2h_bytes
         return {k: v.copy() for k, v in out.items()}
@@ -365,6 +412,12 @@ class PinnedTick:
         self._st = st
 
     def run(self):
+        stream = self.launch()
+        stream.synchronize()
+        return self.outputs
+
+    def launch(self):
+        """Enqueue host->device copy, kernels and device->host copy on the current stream; returns the stream."""
         torch = _torch()
         s, st, n = self.s, self._st, self.n
         stream = torch.cuda.current_stream(s.device)
@@ -381,8 +434,56 @@ class PinnedTick:
             _lib.check(s._lib.bmpc_solve(s._h, n, I("x_fb"), I("phase_k"), I("foot"), I("contact"), O("controls"),
                                          O("states"), O("status"), O("iters"), O("fric_active"), O("resid"), sp))
         st["h_out"][:self.d2h_bytes].copy_(st["d_out"][:self.d2h_bytes], non_blocking=True)
-        stream.synchronize()
-        return self.outputs
+        return stream
+
+
+class ChunkedTick:
+    """A throughput batch from HOST memory in ``chunks`` pieces.  Every chunk has its own solver handle (hence its own work
+    lists and workspace), its own CUDA stream and its own packed pinned staging, and is enqueued as one host->device
+    ``cudaMemcpyAsync`` of its packed inputs, the fused kernels, and one device->host ``cudaMemcpyAsync`` of its packed
+    outputs.  The chunks' streams are independent, so the copies of chunk k+1 / k-1 run under the kernels of chunk k and
+    the kernels of consecutive chunks fill the SMs back to back (the persistent CTAs of chunk k+1 start as those of chunk k
+    run out of work).  Robots are independent (MPC.py:187-304 has no shared state), so chunking changes no result."""
+
+    def __init__(self, solver: BatchedMPC, n: int, chunks: int, lowlevel: bool, want_states: bool, slot: int = 0):
+        if n <= 0 or n > solver.max_batch or chunks < 1 or slot < 0:
+            raise ValueError("batch size / chunk count / slot out of range")
+        from .shard import shard_slice
+        self.s, self.n = solver, n
+        self.slices = [shard_slice(n, i, chunks) for i in range(chunks)]
+        chunk_n = max(sl.stop - sl.start for sl in self.slices)
+        self.children = solver._chunk_solvers(chunks, chunk_n, first=slot * chunks)
+        self.parts = [PinnedTick(c, sl.stop - sl.start, lowlevel, want_states) for c, sl in zip(self.children, self.slices)]
+        self.h2d_bytes = sum(p.h2d_bytes for p in self.parts)
+        self.d2h_bytes = sum(p.d2h_bytes for p in self.parts)
+
+    def set_inputs(self, **arrays):
+        """Copy whole-batch host arrays (x_fb, foot, phase_k, contact, and with lowlevel q, qd, pf_w, t) into the chunks' pinned staging."""
+        for part, sl in zip(self.parts, self.slices):
+            for k, a in arrays.items():
+                part.inputs[k][...] = a[sl]
+
+    def launch(self):
+        torch = _torch()
+        for part, c in zip(self.parts, self.children):
+            with torch.cuda.stream(c._own_stream):
+                part.launch()
+
+    def wait(self):
+        """Block until every chunk of the last ``launch()`` has finished; returns the per-chunk output views (pinned memory,
+        valid until the next launch of this tick)."""
+        for c in self.children:
+            c._own_stream.synchronize()
+        return [p.outputs for p in self.parts]
+
+    def run(self):
+        """``launch()`` + ``wait()``."""
+        self.launch()
+        return self.wait()
+
+    def gather(self):
+        """Whole-batch numpy copies of the outputs of the last ``run()``."""
+        return {k: np.concatenate([p.outputs[k] for p in self.parts], axis=0) for k in self.parts[0].outputs}
 
 
 # ----------------------------------------------------------------------------------------------
