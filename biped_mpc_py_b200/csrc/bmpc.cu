@@ -76,7 +76,8 @@ struct bmpc_handle {
     int opt_lowlat = -1;           // 0 disables the 128-thread walking variant for batches <= 8
     Variant fallback;         // dense re-solve of instances the stage-wise class-1 kernel did not certify (h = 30), or empty
     int* d_lists = nullptr;   // [5][max_batch]: two classes, the h = 30 fallback list, the two lane-residual lists
-    int* d_counts = nullptr;  // [16]: list count i has its dynamic work counter at i + 3 (lists 0-2 and 6-7); 12, 13 lane slice counters
+    int* d_counts = nullptr;  // [24]: list count i has its dynamic work counter at i + 3 (lists 0-2 and 6-7); 12, 13 lane slice counters;
+                              //       16, 17 last-resort list counts with their slice counters at 18, 19
     int64_t launches = 0;
     // closed-loop rollout workspace (allocated on the first bmpc_rollout call, max_batch sized)
     struct {
@@ -156,7 +157,7 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     }
     io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
                  (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
-    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 16 * sizeof(int), st));  // list counts + dynamic work counters
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 24 * sizeof(int), st));  // list counts + dynamic work counters
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
@@ -228,6 +229,25 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         const int fgrid = (std::min(n, f.resident) + f.per_cta - 1) / f.per_cta;
         f.fn<<<fgrid, f.threads, f.smem, st>>>(h->dp, io, h->d_lists + 2 * (size_t)h->max_batch, h->d_counts + 2, f.d_scratch);
         h->launches += 3;
+    }
+    if (n > 8 && (h->lane[0].fn || h->lane[1].fn)) {
+        // Last resort for what is still not certified (status 1 / 2): the lane-per-robot solver with a long polish budget.  A
+        // nearly degenerate instance whose first active-set guesses are far off (one in ~65,000 at h = 30; none seen at h = 10)
+        // walks to the optimal set one row per block and round, which takes more rounds than the kernels above allow.
+        // (Batches of 1 .. 8 robots - the latency path - skip this step.)
+        DevParams last = h->dp;
+        last.polish_rounds = 128;
+        last.lane_sync = 0;
+        for (int b = 0; b < 2; ++b) {
+            LaneVariant& lv = h->lane[b];
+            if (!lv.fn) continue;
+            if (!lv.d_ws) CUDA_TRY(cudaMalloc(&lv.d_ws, sizeof(double) * lv.ws_doubles));
+            int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
+            collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_lists + (size_t)b * h->max_batch, h->d_counts + b, io.status, rlist,
+                                                                       h->d_counts + 16 + b);
+            lv.fn<<<std::min(lv.grid, 8), lv.threads, lv.smem, st>>>(last, io, rlist, h->d_counts + 16 + b, h->d_counts + 18 + b, lv.d_ws, 1);
+            h->launches += 2;
+        }
     }
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[5], st));
     h->launches += 1;  // classify
@@ -357,7 +377,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         return 1;
     }
     e = cudaMalloc(&h->d_lists, sizeof(int) * 5 * (size_t)max_batch);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 24);
     if (e != cudaSuccess) {
         cudaFree(h->d_lists);
         delete h;

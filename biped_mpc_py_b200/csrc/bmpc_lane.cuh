@@ -1144,7 +1144,7 @@ struct LaneSolver {
         int round = 0;
 #pragma unroll 1
         while (group_any(pol)) {
-            if (pol && round >= p.polish_rounds) pol = false;
+            if (pol && round >= (HZ > 10 ? 3 : 1) * p.polish_rounds) pol = false;  // (long horizons: more weakly active rows to walk through)
             ++round;
             double pv[12];
             if (pol) {
@@ -1162,6 +1162,9 @@ struct LaneSolver {
                     for (int e = 0; e < LB * LB; ++e) r[L::o_Nn + e] = Nl[e];
                 }
                 if (bad_blk) pol = false;
+#ifdef BMPC_LANE_DEBUG
+                printf("[polish] round %d bad_blk %d\n", round, (int)bad_blk);
+#endif
             }
             if (pol) {
                 grad(L::o_pp, L::o_tv, nullptr);
@@ -1188,7 +1191,12 @@ struct LaneSolver {
                 for (int a = 0; a < LB; ++a)
 #pragma unroll
                     for (int b = 0; b <= a; ++b) G[tri(a, b)] = (a == b) ? Rw(l, a) : 0.0;
-                if (!factor_stage<true>(v, r, G, rhs, pv, L::o_xv, N, dim)) pol = false;
+                if (!factor_stage<true>(v, r, G, rhs, pv, L::o_xv, N, dim)) {
+                    pol = false;
+#ifdef BMPC_LANE_DEBUG
+                    printf("[polish] round %d factor breakdown at block %d (dim %d)\n", round, v, dim);
+#endif
+                }
             }
             bool changed = false;
             {
@@ -1223,6 +1231,9 @@ struct LaneSolver {
                     });
                     if (ch) r[L::o_am] = (double)mk, changed = true;
                 }
+#ifdef BMPC_LANE_DEBUG
+                if (pol) printf("[polish] round %d primal: changed %d\n", round, (int)changed);
+#endif
             }
             if (pol && !changed) {
                 // dual check: minus the gradient must be a non-negative combination of the active rows
@@ -1239,10 +1250,20 @@ struct LaneSolver {
                     unsigned drop = 0u;
                     if (block_dual_fast<LB>(Cb, mb, mk, lam, rneg, gs)) continue;
                     if (!block_dual_check<LB>(Cb, mb, mk, rneg, gs, &drop)) {
+                        // releasing several rows of many blocks at once can cycle (release, re-add as violated, release ...):
+                        // after the first rounds only one row per block is released at a time
+                        if (round > 3 && drop != 0u) drop &= (~drop + 1u);
                         if (drop == 0u) fail = true;
                         else r[L::o_am] = (double)(mk & ~drop), changed = true;
+#ifdef BMPC_LANE_DEBUG
+                        printf("[polish] round %d block %d mask 0x%x dual check: drop 0x%x rneg %.3e %.3e %.3e %.3e %.3e gs %.3e\n", round, v, mk, drop,
+                               rneg[0], rneg[1], rneg[2], rneg[3], rneg[4], gs);
+#endif
                     }
                 }
+#ifdef BMPC_LANE_DEBUG
+                printf("[polish] round %d dual: fail %d changed %d\n", round, (int)fail, (int)changed);
+#endif
                 if (fail) pol = false;
                 else if (!changed) polished = true, pol = false;
             }

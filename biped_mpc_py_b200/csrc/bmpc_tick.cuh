@@ -1216,7 +1216,9 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                 gsync<NT>();
                 }
                 bool ok = false;
-                const int max_rounds = attempt < 0 ? p.warm_rounds : p.polish_rounds;
+                // the last attempt may take six times the rounds: a nearly degenerate instance whose first active-set guesses are
+                // far off (one in ~65,000 at h = 30) walks to the optimal set one row per block and round (see the release rule below)
+                const int max_rounds = attempt < 0 ? p.warm_rounds : (attempt == 2 ? 6 * p.polish_rounds : p.polish_rounds);
                 for (int round = 0; round < max_rounds; ++round) {
                     lock_sync();
                     // per block: affine set of the active rows  u_b = p_b + N_b w_b
@@ -1326,6 +1328,9 @@ __global__ void __launch_bounds__(NT * NW) mpc_tick2_kernel(const __grid_constan
                         unsigned drop = 0u;
                         if (block_dual_fast<LB>(Cb, mb, (unsigned)amask[j], r_l + j * mb, rneg, gs)) continue;
                         if (!block_dual_check<LB>(Cb, mb, (unsigned)amask[j], rneg, gs, &drop)) {
+                            // releasing several rows of many blocks at once can cycle (release, re-add as violated, release ...):
+                            // after the first rounds only one row per block is released at a time
+                            if (round > 3 && drop != 0u) drop &= (~drop + 1u);
                             if (drop == 0u) fail = 1;
                             else amask[j] &= ~(int)drop, changed = 1;
                         }

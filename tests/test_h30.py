@@ -144,3 +144,22 @@ def test_h30_lane_per_robot_front_end_matches_warp_kernels():
     du = np.abs(out["controls"] - ref["controls"]).reshape(n, -1).max(axis=1) / scale
     assert du.max() <= 1e-6, du.max()
     assert np.abs(out["tau"] - ref["tau"]).max() <= 1e-6
+
+
+def test_h30_nearly_degenerate_instance_is_certified():
+    """Regression (round-1 gap): instance 6464 of synthetic shard 1000 at h = 30 (standing) was returned uncertified (status 1)
+    by every kernel - its polish cycled between releasing and re-adding rows of ten blocks at once.  With the one-row-per-block
+    release rule and the last-resort pass it is certified and agrees with the oracle, inside a small batch (warp-per-robot
+    kernels first, then the last resort) and inside a batch that takes the lane-per-robot kernels."""
+    from oracle import reference_mpc as rm
+    from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
+    mpc = MPC(h=30)
+    b = synth.make_batch(65536, shard_index=1000, mpc=mpc, extend=True)
+    i = 6464
+    _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], rm.MPCParams(h=30), rm.BipedParams(), b["contact"][i], extend=True)
+    for lo, hi in ((i - 32, i + 32), (i - 2048, i + 2048)):
+        s = BatchedMPC(mpc, Biped(), max_batch=hi - lo, extend_gait=True)
+        out = s.step_host(*[b[k][lo:hi] for k in ("x_fb", "t", "foot", "contact", "q", "qd", "pf_w")], phase_k=b["phase_k"][lo:hi])
+        assert (out["status"] == 0).all(), np.nonzero(out["status"])[0]
+        assert np.abs(out["controls"][i - lo] - u).max() / max(1.0, np.abs(u).max()) <= 1e-5
+        s.close()
