@@ -502,6 +502,17 @@ def default_solver(mpc, biped, max_batch: int = 1, extend_gait: bool = False) ->
     return s
 
 
+def _check_status(who: str, status: int):
+    """The reference never looks at its solver's status (MPC.py:297-300); here a result that is not the certified optimum is
+    never passed on silently: bad input raises, an uncertified iterate warns."""
+    if status == STATUS_BADINPUT:
+        raise ValueError(f"{who}: non-finite input or singular euler-rate matrix (pitch = +-pi/2)")
+    if status != STATUS_OPTIMAL:
+        import warnings
+        warnings.warn(f"{who}: the returned point is an interior-point iterate that was NOT certified optimal (status {status})",
+                      RuntimeWarning, stacklevel=3)
+
+
 def solve_mpc(x_fb, t, foot, mpc, biped, contact):
     """Drop-in for ``solve_mpc`` (MPC.py:187-304): returns ``(states (h,13), controls (h,12))``.
 
@@ -515,10 +526,13 @@ def solve_mpc(x_fb, t, foot, mpc, biped, contact):
         raise IndexError(f"contact must have shape ({h}, 2), got {contact.shape} "
                          "(the reference fails the same way for h != 10 walking, MPC.py:58)")
     s = default_solver(mpc, biped)
-    out = s.solve_host(np.asarray(x_fb, dtype=np.float64).reshape(1, 12), np.array([float(t)]),
-                       np.asarray(foot, dtype=np.float64).reshape(1, 6), (contact != 0).astype(np.uint8)[None])
-    if int(out["status"][0]) == STATUS_BADINPUT:
-        raise ValueError("solve_mpc: non-finite input or singular euler-rate matrix (pitch = +-pi/2)")
+    args = (np.asarray(x_fb, dtype=np.float64).reshape(1, 12), np.array([float(t)]),
+            np.asarray(foot, dtype=np.float64).reshape(1, 6), (contact != 0).astype(np.uint8)[None])
+    out = s.solve_host(*args)
+    if int(out["status"][0]) in (STATUS_MAXITER, STATUS_NUMERIC):
+        # the latency path (batches of 1 .. 8) skips the last-resort pass of the library: repeat the instance in a batch that has it
+        out = default_solver(mpc, biped, max_batch=16).solve_host(*[np.repeat(a, 9, axis=0) for a in args])
+    _check_status("solve_mpc", int(out["status"][0]))
     return out["states"][0], out["controls"][0]
 
 
@@ -550,7 +564,10 @@ def mpc_tick(x_fb, t, q, qd, mpc, biped, gait: int = 1):
     s = default_solver(mpc, biped)
     out = s.tick_host(np.asarray(x_fb, dtype=np.float64).reshape(1, 12), np.array([float(t)]), np.asarray(q).reshape(1, 10),
                       np.asarray(qd).reshape(1, 10), np.array([int(gait)]), want_states=True)
-    if int(out["status"][0]) == STATUS_BADINPUT:
-        raise ValueError("mpc_tick: non-finite input or singular euler-rate matrix (pitch = +-pi/2)")
+    if int(out["status"][0]) in (STATUS_MAXITER, STATUS_NUMERIC):  # (see solve_mpc)
+        rep9 = lambda a: np.repeat(np.asarray(a).reshape(1, -1), 9, axis=0)
+        out = default_solver(mpc, biped, max_batch=16).tick_host(rep9(x_fb), np.full(9, float(t)), rep9(q), rep9(qd), np.full(9, int(gait)),
+                                                                 want_states=True)
+    _check_status("mpc_tick", int(out["status"][0]))
     return dict(states=out["states"][0], controls=out["controls"][0], tau=out["tau"][0].reshape(10, 1),
                 pf_w=out["pf_w"][0].reshape(6, 1), contact=out["contact"][0])

@@ -163,3 +163,21 @@ def test_h30_nearly_degenerate_instance_is_certified():
         assert (out["status"] == 0).all(), np.nonzero(out["status"])[0]
         assert np.abs(out["controls"][i - lo] - u).max() / max(1.0, np.abs(u).max()) <= 1e-5
         s.close()
+
+
+def test_h30_reference_signature_retries_through_the_last_resort():
+    """The same instance through the drop-in ``solve_mpc`` (one robot: the latency path, which skips the last-resort pass): the
+    shim repeats it in a small batch and returns the certified optimum without a warning."""
+    import warnings
+    import biped_mpc_py_b200 as bm
+    from oracle import reference_mpc as rm
+    from biped_mpc_py_b200 import synth
+    mpc = bm.MPC(h=30)
+    b = synth.make_batch(65536, shard_index=1000, mpc=mpc, extend=True)
+    i = 6464
+    assert b["gait"][i] == 0  # standing: reference-defined at h = 30 (no gait extension needed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        states, controls = bm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, bm.Biped(), b["contact"][i])
+    _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], rm.MPCParams(h=30), rm.BipedParams(), b["contact"][i], extend=True)
+    assert np.abs(controls - u).max() / max(1.0, np.abs(u).max()) <= 1e-5
