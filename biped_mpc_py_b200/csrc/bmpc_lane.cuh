@@ -710,12 +710,118 @@ struct LaneSolver {
         return part;
     }
 
+    // ---- per-block active-set algebra of the polish, on the structural rows (same mathematics as block_nullspace /
+    //      block_dual_fast of bmpc_polish.cuh, which serve the warp-per-robot kernels from a dense row matrix; here the rows are
+    //      code, every row is visited by every lane with a 0 / 1 weight, and nothing is indexed at run time, so the 32 robots of
+    //      a warp stay on one path and nothing lives in local memory).  Bit k of `mk` = k-th surviving row. ------------------
+    BMPC_HD __forceinline__ void active_normal(unsigned mk, const double (&rhs)[LB], double (&A)[LB][LB + 1], int (&perm)[LB], int& np) const {
+        double G[15];
+#pragma unroll
+        for (int e = 0; e < 15; ++e) G[e] = 0.0;
+        for_rows([&](auto tag, int, int k) { rrank(tag, G, ((mk >> k) & 1u) ? 1.0 : 0.0); });
+#pragma unroll
+        for (int a = 0; a < LB; ++a) {
+#pragma unroll
+            for (int b = 0; b <= a; ++b) A[a][b] = G[tri(a, b)], A[b][a] = G[tri(a, b)];
+            A[a][LB] = rhs[a];
+        }
+        gauss_jordan_diag<LB>(A, perm, np);
+    }
+    // position space -> component space: out[c] = A[i][LB] of the pivot position i with perm[i] == c, 0 for a free component
+    static BMPC_HD __forceinline__ void unpermute(const double (&A)[LB][LB + 1], const int (&perm)[LB], int np, double (&out)[LB]) {
+#pragma unroll
+        for (int c = 0; c < LB; ++c) {
+            double x = 0.0;
+#pragma unroll
+            for (int i = 0; i < LB; ++i) x = (i < np && perm[i] == c) ? A[i][LB] : x;
+            out[c] = x;
+        }
+    }
+    // affine set {x : C_A x = b_A} of the active rows: particular solution -> o_pp, basis -> o_Nn, dimension -> o_dim of the
+    // record; false if the rows are inconsistent
+    BMPC_HD __forceinline__ bool blk_nullspace(SV r, unsigned mk) const {
+        double rhs[LB];
+#pragma unroll
+        for (int c = 0; c < LB; ++c) rhs[c] = 0.0;
+        double bmax = 1.0;
+        for_rows([&](auto tag, int, int k) {
+            const bool on = ((mk >> k) & 1u) != 0u;
+            const double bk = rrhs(tag);
+            bmax = on ? fmax(bmax, fabs(bk)) : bmax;
+            radd(tag, rhs, on ? bk : 0.0);
+        });
+        double A[LB][LB + 1];
+        int perm[LB], np;
+        active_normal(mk, rhs, A, perm, np);
+        double p5[LB];
+        unpermute(A, perm, np, p5);
+#pragma unroll
+        for (int c = 0; c < LB; ++c) r[L::o_pp + c] = p5[c];
+        // basis: column a = q - np of N for every free position q (the record is this lane's own memory: run-time offsets are fine)
+#pragma unroll
+        for (int e = 0; e < LB * LB; ++e) r[L::o_Nn + e] = 0.0;
+#pragma unroll
+        for (int q = 0; q < LB; ++q)
+            if (q >= np) {
+#pragma unroll
+                for (int i = 0; i < LB; ++i) r[L::o_Nn + perm[i] * LB + (q - np)] = (i < np) ? -A[i][q] : ((i == q) ? 1.0 : 0.0);
+            }
+        r[L::o_dim] = (double)(LB - np);
+        bool ok = true;
+        for_rows([&](auto tag, int, int k) {
+            const bool on = ((mk >> k) & 1u) != 0u;
+            if (on && fabs(rdot(tag, p5) - rrhs(tag)) > 1e-7 * bmax) ok = false;
+        });
+        return ok;
+    }
+    // fast multiplier check (block_dual_fast): y = lam + C_A z with G z = r - C_A' lam reproduces r = -(gradient, at o_tv)
+    // exactly and stays close to the interior-point multipliers (at o_l); true if y >= 0 and C_A' y = r
+    BMPC_HD __forceinline__ bool blk_dual_fast(SV r, unsigned mk, double gscale) const {
+        double rr[LB], rho[LB], lv[NR];
+#pragma unroll
+        for (int c = 0; c < LB; ++c) rr[c] = -r[L::o_tv + c], rho[c] = rr[c];
+        for_rows([&](auto tag, int slot, int k) {
+            lv[slot] = r[L::o_l + slot];
+            radd(tag, rho, ((mk >> k) & 1u) ? -lv[slot] : 0.0);
+        });
+        double A[LB][LB + 1];
+        int perm[LB], np;
+        active_normal(mk, rho, A, perm, np);
+        double z5[LB];
+        unpermute(A, perm, np, z5);
+        bool ok = true;
+        for_rows([&](auto tag, int slot, int k) {
+            const bool on = ((mk >> k) & 1u) != 0u;
+            const double y = lv[slot] + rdot(tag, z5);
+            if (on && !(y >= 0.0)) ok = false;
+            radd(tag, rr, on ? -y : 0.0);
+        });
+        double rmax = 0.0;
+#pragma unroll
+        for (int c = 0; c < LB; ++c) rmax = fmax(rmax, fabs(rr[c]));
+        return ok && rmax <= 1e-9 * gscale;
+    }
+    // exact multiplier check of one block (rare: only when the fast check is undecided): Lawson-Hanson NNLS of bmpc_polish.cuh
+    // on a dense copy of the rows, built here so that the dense copy is only touched on this path
+    BMPC_HD __forceinline__ bool blk_dual_exact(SV r, unsigned mk, double gscale, unsigned* drop) const {
+        double Cb[NR * LB], rneg[LB];
+        for_rows([&](auto tag, int, int k) {
+            double c5[LB];
+            rcoef(tag, c5);
+#pragma unroll
+            for (int c = 0; c < LB; ++c) Cb[k * LB + c] = c5[c];
+        });
+#pragma unroll
+        for (int c = 0; c < LB; ++c) rneg[c] = -r[L::o_tv + c];
+        return block_dual_check<LB>(Cb, p.mb, mk, rneg, gscale, drop);
+    }
+
     // ---- group synchronisation: the warps of a CTA can run in lockstep (p.lane_sync: 0 none, 1 per iteration / phase, 2 also per
     //      stage of every sweep) so that they fetch the same instructions at the same time.  Every thread of the group takes
     //      the same control path; `act`-style flags, not returns, switch a lane off. ------------------------------------
     BMPC_HD __forceinline__ bool group_any(bool x) const {
 #ifdef __CUDA_ARCH__
-        if (p.lane_sync) return __syncthreads_or(x) != 0;
+        if (p.lane_sync & 3) return __syncthreads_or(x) != 0;
         return __any_sync(0xffffffffu, x) != 0;
 #else
         return x;
@@ -723,7 +829,22 @@ struct LaneSolver {
     }
     BMPC_HD __forceinline__ void stage_sync() const {
 #ifdef __CUDA_ARCH__
-        if (p.lane_sync >= 2) __syncthreads();
+        if ((p.lane_sync & 3) >= 2) __syncthreads();
+#endif
+    }
+    // the polish: in lockstep like the interior point, or (p.lane_sync & 4) every warp on its own - the number of polish rounds
+    // differs from robot to robot, and a CTA in lockstep runs the rounds of its slowest robot
+    BMPC_HD __forceinline__ bool group_any_polish(bool x) const {
+#ifdef __CUDA_ARCH__
+        if ((p.lane_sync & 3) && !(p.lane_sync & 4)) return __syncthreads_or(x) != 0;
+        return __any_sync(0xffffffffu, x) != 0;
+#else
+        return x;
+#endif
+    }
+    BMPC_HD __forceinline__ void stage_sync_polish() const {
+#ifdef __CUDA_ARCH__
+        if ((p.lane_sync & 3) >= 2 && !(p.lane_sync & 4)) __syncthreads();
 #endif
     }
 
@@ -1074,7 +1195,6 @@ struct LaneSolver {
 
         // ---- 3. active-set polish + certificate (one attempt; anything else goes to the warp-per-robot kernels) ----
         bool pol = act && status == 0, polished = false;
-        double Cb[NR * LB], rb[NR];  // dense copy of the block rows for the per-block null-space / multiplier functions (polish only)
         if (pol) {
             // diag(Hc) from the uncontrolled cost-to-go (into tv)
             init_P();
@@ -1132,18 +1252,11 @@ struct LaneSolver {
                 });
                 r[L::o_am] = (double)mk;
             }
-            for_rows([&](auto tag, int, int k) {
-                double c5[LB];
-                rcoef(tag, c5);
-#pragma unroll
-                for (int c = 0; c < LB; ++c) Cb[k * LB + c] = c5[c];
-                rb[k] = rrhs(tag);
-            });
             status = 1;
         }
         int round = 0;
 #pragma unroll 1
-        while (group_any(pol)) {
+        while (group_any_polish(pol)) {
             if (pol && round >= (HZ > 10 ? 3 : 1) * p.polish_rounds) pol = false;  // (long horizons: more weakly active rows to walk through)
             ++round;
             double pv[12];
@@ -1152,14 +1265,7 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
                     SV r = rec(v);
-                    double pl[LB], Nl[LB * LB];
-                    int dim = 0;
-                    if (!block_nullspace<LB>(Cb, rb, mb, (unsigned)r[L::o_am], pl, Nl, &dim)) bad_blk = true;
-                    r[L::o_dim] = (double)dim;
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) r[L::o_pp + c] = pl[c];
-#pragma unroll
-                    for (int e = 0; e < LB * LB; ++e) r[L::o_Nn + e] = Nl[e];
+                    if (!blk_nullspace(r, (unsigned)r[L::o_am])) bad_blk = true;
                 }
                 if (bad_blk) pol = false;
 #ifdef BMPC_LANE_DEBUG
@@ -1175,7 +1281,7 @@ struct LaneSolver {
             }
 #pragma unroll 1
             for (int v = S - 1; v >= 0; --v) {
-                stage_sync();
+                stage_sync_polish();
                 if (!pol) continue;
                 prefetch_rec(v - 1, L::REC);
                 SV r = rec(v);
@@ -1205,7 +1311,7 @@ struct LaneSolver {
                 for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
-                    stage_sync();
+                    stage_sync_polish();
                     if (!pol) continue;
                     prefetch_rec(v + 1, L::REC);
                     SV r = rec(v);
@@ -1242,22 +1348,17 @@ struct LaneSolver {
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
                     SV r = rec(v);
-                    double rneg[LB], lam[NR];
-#pragma unroll
-                    for (int c = 0; c < LB; ++c) rneg[c] = -r[L::o_tv + c];
-                    for_rows([&](auto, int slot, int k) { lam[k] = r[L::o_l + slot]; });
-                    unsigned mk = (unsigned)r[L::o_am];
+                    const unsigned mk = (unsigned)r[L::o_am];
                     unsigned drop = 0u;
-                    if (block_dual_fast<LB>(Cb, mb, mk, lam, rneg, gs)) continue;
-                    if (!block_dual_check<LB>(Cb, mb, mk, rneg, gs, &drop)) {
+                    if (blk_dual_fast(r, mk, gs)) continue;
+                    if (!blk_dual_exact(r, mk, gs, &drop)) {
                         // releasing several rows of many blocks at once can cycle (release, re-add as violated, release ...):
                         // after the first rounds only one row per block is released at a time
                         if (round > 3 && drop != 0u) drop &= (~drop + 1u);
                         if (drop == 0u) fail = true;
                         else r[L::o_am] = (double)(mk & ~drop), changed = true;
 #ifdef BMPC_LANE_DEBUG
-                        printf("[polish] round %d block %d mask 0x%x dual check: drop 0x%x rneg %.3e %.3e %.3e %.3e %.3e gs %.3e\n", round, v, mk, drop,
-                               rneg[0], rneg[1], rneg[2], rneg[3], rneg[4], gs);
+                        printf("[polish] round %d block %d mask 0x%x dual check: drop 0x%x gs %.3e\n", round, v, mk, drop, gs);
 #endif
                     }
                 }
@@ -1377,7 +1478,7 @@ __global__ void __launch_bounds__(256, 1) lane_tick_kernel(const __grid_constant
     SV ps{lane_smem + (size_t)wib * L::smem_doubles * 32 + lane};
     while (true) {
         int base = 0;
-        if (p.lane_sync) {
+        if (p.lane_sync & 3) {
             __syncthreads();  // (everybody has read s_base of the previous round)
             if (threadIdx.x == 0) s_base = atomicAdd(slice_counter, 32 * nw);
             __syncthreads();

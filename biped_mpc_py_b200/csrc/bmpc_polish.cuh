@@ -23,34 +23,15 @@ namespace bmpc {
 // pivoting.  The pivot is moved to position `step` by predicated swaps, so every register index
 // is a compile-time constant (no local memory); perm[] maps positions back to components and the
 // first *np positions are the pivots.  A[i][LB] is the transformed right-hand side.
+//
+// gauss_jordan_diag: A holds the full symmetric matrix and the right-hand side in column LB on entry.
 template <int LB>
-BMPC_HD __forceinline__ void normal_reduce(const double* __restrict__ Cb, int mb, unsigned mask,
-                                              const double (&rhs)[LB], double (&A)[LB][LB + 1], int (&perm)[LB],
-                                              int& np) {
-#pragma unroll
-    for (int a = 0; a < LB; ++a) {
-#pragma unroll
-        for (int b = 0; b < LB; ++b) A[a][b] = 0.0;
-        A[a][LB] = rhs[a];
-        perm[a] = a;
-    }
-#pragma unroll 1
-    for (int k = 0; k < mb; ++k)
-        if ((mask >> k) & 1u) {
-            double cb[LB];
-#pragma unroll
-            for (int c = 0; c < LB; ++c) cb[c] = Cb[k * LB + c];
-#pragma unroll
-            for (int a = 0; a < LB; ++a)
-#pragma unroll
-                for (int b = 0; b <= a; ++b) A[a][b] += cb[a] * cb[b];
-        }
+BMPC_HD __forceinline__ void gauss_jordan_diag(double (&A)[LB][LB + 1], int (&perm)[LB], int& np) {
     double scale = 1e-300;
 #pragma unroll
     for (int a = 0; a < LB; ++a) {
         scale = fmax(scale, A[a][a]);
-#pragma unroll
-        for (int b = 0; b < a; ++b) A[b][a] = A[a][b];
+        perm[a] = a;
     }
     np = 0;
     bool done = false;
@@ -96,6 +77,34 @@ BMPC_HD __forceinline__ void normal_reduce(const double* __restrict__ Cb, int mb
             ++np;
         }
     }
+}
+
+template <int LB>
+BMPC_HD __forceinline__ void normal_reduce(const double* __restrict__ Cb, int mb, unsigned mask,
+                                              const double (&rhs)[LB], double (&A)[LB][LB + 1], int (&perm)[LB],
+                                              int& np) {
+#pragma unroll
+    for (int a = 0; a < LB; ++a) {
+#pragma unroll
+        for (int b = 0; b < LB; ++b) A[a][b] = 0.0;
+        A[a][LB] = rhs[a];
+    }
+#pragma unroll 1
+    for (int k = 0; k < mb; ++k)
+        if ((mask >> k) & 1u) {
+            double cb[LB];
+#pragma unroll
+            for (int c = 0; c < LB; ++c) cb[c] = Cb[k * LB + c];
+#pragma unroll
+            for (int a = 0; a < LB; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) A[a][b] += cb[a] * cb[b];
+        }
+#pragma unroll
+    for (int a = 0; a < LB; ++a)
+#pragma unroll
+        for (int b = 0; b < a; ++b) A[b][a] = A[a][b];
+    gauss_jordan_diag<LB>(A, perm, np);
 }
 
 // Affine set {x : C_A x = b_A} of the active rows of one block: p[LB] particular solution (free
