@@ -25,8 +25,56 @@ namespace bmpc {
 // first *np positions are the pivots.  A[i][LB] is the transformed right-hand side.
 //
 // gauss_jordan_diag: A holds the full symmetric matrix and the right-hand side in column LB on entry.
+// One elimination step is a function template of the step number (called LB times below): with the step a compile-time
+// constant every index into A and perm is one too, and the arrays are scalarised into registers (as a `#pragma unroll` loop
+// over the steps the compiler kept the loop and put A and perm into local memory).
+template <int LB, int STEP>
+BMPC_HD __forceinline__ void gauss_jordan_step(double (&A)[LB][LB + 1], int (&perm)[LB], int& np, bool& done, double scale) {
+    int pv = STEP;
+    double best = A[STEP][STEP];
+#pragma unroll
+    for (int c = STEP + 1; c < LB; ++c) {
+        const bool gt = A[c][c] > best;
+        best = gt ? A[c][c] : best;
+        pv = gt ? c : pv;
+    }
+    const bool take = !done && best > 1e-12 * scale;
+    done = done || !take;
+#pragma unroll
+    for (int c = STEP + 1; c < LB; ++c) {
+        const bool sw = take && (pv == c);
+#pragma unroll
+        for (int col = 0; col <= LB; ++col) {
+            const double t = A[STEP][col];
+            A[STEP][col] = sw ? A[c][col] : t;
+            A[c][col] = sw ? t : A[c][col];
+        }
+#pragma unroll
+        for (int row = 0; row < LB; ++row) {
+            const double t = A[row][STEP];
+            A[row][STEP] = sw ? A[row][c] : t;
+            A[row][c] = sw ? t : A[row][c];
+        }
+        const int tp = perm[STEP];
+        perm[STEP] = sw ? perm[c] : tp;
+        perm[c] = sw ? tp : perm[c];
+    }
+    // (branch-free: a step that is not taken multiplies by 1 and subtracts 0)
+    const double inv = take ? 1.0 / A[STEP][STEP] : 1.0;
+#pragma unroll
+    for (int col = 0; col <= LB; ++col) A[STEP][col] *= inv;
+#pragma unroll
+    for (int r = 0; r < LB; ++r)
+        if (r != STEP) {
+            const double f = take ? A[r][STEP] : 0.0;
+#pragma unroll
+            for (int col = 0; col <= LB; ++col) A[r][col] -= f * A[STEP][col];
+        }
+    np += take ? 1 : 0;
+}
 template <int LB>
 BMPC_HD __forceinline__ void gauss_jordan_diag(double (&A)[LB][LB + 1], int (&perm)[LB], int& np) {
+    static_assert(LB == 5 || LB == 6, "one step call per component below");
     double scale = 1e-300;
 #pragma unroll
     for (int a = 0; a < LB; ++a) {
@@ -35,48 +83,12 @@ BMPC_HD __forceinline__ void gauss_jordan_diag(double (&A)[LB][LB + 1], int (&pe
     }
     np = 0;
     bool done = false;
-#pragma unroll
-    for (int step = 0; step < LB; ++step) {
-        int pv = step;
-        double best = A[step][step];
-#pragma unroll
-        for (int c = step + 1; c < LB; ++c)
-            if (A[c][c] > best) best = A[c][c], pv = c;
-        const bool take = !done && best > 1e-12 * scale;
-        done = done || !take;
-#pragma unroll
-        for (int c = step + 1; c < LB; ++c) {
-            const bool sw = take && (pv == c);
-#pragma unroll
-            for (int col = 0; col <= LB; ++col) {
-                const double t = A[step][col];
-                A[step][col] = sw ? A[c][col] : t;
-                A[c][col] = sw ? t : A[c][col];
-            }
-#pragma unroll
-            for (int row = 0; row < LB; ++row) {
-                const double t = A[row][step];
-                A[row][step] = sw ? A[row][c] : t;
-                A[row][c] = sw ? t : A[row][c];
-            }
-            const int tp = perm[step];
-            perm[step] = sw ? perm[c] : tp;
-            perm[c] = sw ? tp : perm[c];
-        }
-        if (take) {
-            const double inv = 1.0 / A[step][step];
-#pragma unroll
-            for (int col = 0; col <= LB; ++col) A[step][col] *= inv;
-#pragma unroll
-            for (int r = 0; r < LB; ++r)
-                if (r != step) {
-                    const double f = A[r][step];
-#pragma unroll
-                    for (int col = 0; col <= LB; ++col) A[r][col] -= f * A[step][col];
-                }
-            ++np;
-        }
-    }
+    gauss_jordan_step<LB, 0>(A, perm, np, done, scale);
+    gauss_jordan_step<LB, 1>(A, perm, np, done, scale);
+    gauss_jordan_step<LB, 2>(A, perm, np, done, scale);
+    gauss_jordan_step<LB, 3>(A, perm, np, done, scale);
+    gauss_jordan_step<LB, 4>(A, perm, np, done, scale);
+    if constexpr (LB == 6) gauss_jordan_step<LB, 5>(A, perm, np, done, scale);
 }
 
 template <int LB>
