@@ -9,7 +9,8 @@ CPU fallback - importing works anywhere, computing requires a B200 and the built
 from .params import MPC, Biped, pack_params
 from .gait import gait_phase, get_contact_sequence
 from .api import BatchedMPC, solve_mpc, lowLevelControl, getFootPositionWorld, default_solver, mpc_tick
+from .sim import SimulatorAdapter
 from . import synth
 
 __all__ = ["MPC", "Biped", "pack_params", "gait_phase", "get_contact_sequence", "BatchedMPC", "solve_mpc",
-           "lowLevelControl", "getFootPositionWorld", "default_solver", "mpc_tick", "synth"]
+           "lowLevelControl", "getFootPositionWorld", "default_solver", "mpc_tick", "SimulatorAdapter", "synth"]

@@ -97,6 +97,21 @@ class BatchedMPC:
         for c in self._children:
             c.set_option(name, value)
 
+    def pin_kernel_family(self, family: str = "auto"):
+        """Which kernel family solves a robot.  ``"auto"`` (default): decided per call from the batch and class sizes (size
+        gates of bmpc.cu::setup_lanes; small batches and small classes run on the warp-per-robot kernels, large ones on the
+        lane-per-robot kernels with their later passes) - fastest, but the family, and with it the last bits of the result
+        (<= 1e-11 relative, 3e-7 on one robot in a million), depend on how the caller shards its robots.  ``"lane"`` /
+        ``"warp"``: every robot takes the same code path whatever the batch it arrives in, so results are bit-identical
+        for any sharding or GPU count (``"lane"`` needs the reference's limit structure, five free inputs per foot)."""
+        if family not in ("auto", "lane", "warp"):
+            raise ValueError("family must be 'auto', 'lane' or 'warp'")
+        # -1 = the built-in size gates
+        self.set_option("lane_mode", 0 if family == "warp" else -1)
+        self.set_option("lane_min", 1 if family == "lane" else -1)
+        self.set_option("lane_defer_min", 1 if family == "lane" else -1)
+        self.set_option("lowlat", 0 if family != "auto" else -1)
+
     def warm_start(self, on: bool = True):
         """Warm start across consecutive ``step`` / ``solve`` calls of a caller-owned control loop: robot i of the
         batch must be the same robot one tick later.  Same certified optimum as the cold solve, ~3x faster ticks."""

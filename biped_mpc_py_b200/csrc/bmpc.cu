@@ -33,6 +33,25 @@ int fail(const std::string& msg) {
         if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// Every entry point works on the handle's device and leaves the caller's current device as it found it (a multi-GPU host
+// process may call a handle of device k from a thread whose current device is another one).
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int d) : dev(d) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(d)          \
+    DeviceGuard _guard(d);    \
+    CUDA_TRY(_guard.err)
+
 typedef void (*TickKernel)(const DevParams, const IoPtrs, const int*, const int*, double*);
 
 // lane-per-robot front end of one class (bmpc_lane.cuh): what it certifies is done, the rest goes to the class's Variant
@@ -44,6 +63,12 @@ struct LaneVariant {
     size_t ws_doubles = 0;
     int min_count = 0;       // classes smaller than this stay on the warp-per-robot kernel (decided on the device)
     double* d_ws = nullptr;  // [warps][blocks][record][32] lane-interleaved block records
+    // second polish pass (LaneDefer, bmpc_lane_api.h): store of the parked robots
+    int defer_floats = 0, defer_cap = 0, ipm_floats = 0, ipm_cap = 0;
+    float* d_defer = nullptr;
+    int* d_defer_list = nullptr;
+    float* d_ipm = nullptr;
+    int* d_ipm_list = nullptr;
 };
 
 struct Variant {
@@ -74,9 +99,14 @@ struct bmpc_handle {
     int opt_lane_ctas_per_sm = -1; // resident CTAs per SM of the lane kernels
     int opt_lane_warps = -1;       // warps (32 robots each) per CTA
     int opt_lowlat = -1;           // 0 disables the 128-thread walking variant for batches <= 8
+    int opt_lane_ipm_inline = -1;     // interior-point iterations of the first lane pass before a robot is parked (0: never)
+    int opt_lane_defer_min = -1;      // smallest class that uses the second pass (-1: two waves of slices)
+    int opt_lane_inline_rounds = -1;  // polish rounds of the first lane pass before a robot is parked for the second (0: one pass)
     Variant fallback;         // dense re-solve of instances the stage-wise class-1 kernel did not certify (h = 30), or empty
     int* d_lists = nullptr;   // [5][max_batch]: two classes, the h = 30 fallback list, the two lane-residual lists
-    int* d_counts = nullptr;  // [24]: list count i has its dynamic work counter at i + 3 (lists 0-2 and 6-7); 12, 13 lane slice counters;
+    int* d_counts = nullptr;  // [32]: list count i has its dynamic work counter at i + 3 (lists 0-2 and 6-7); 12, 13 lane slice counters; 20, 21 parked
+                              //       robots (polish) of the lane kernels
+                              //       with the polish pass's slice counters at 22, 23; 24, 25 parked robots (interior point), slice counters at 26, 27;
                               //       16, 17 last-resort list counts with their slice counters at 18, 19
     int64_t launches = 0;
     // closed-loop rollout workspace (allocated on the first bmpc_rollout call, max_batch sized)
@@ -91,7 +121,8 @@ struct bmpc_handle {
         int32_t* ws_mask = nullptr;
     } ro;
     int warm_enabled = 0;        // bmpc_warm_start: bmpc_step / bmpc_solve start from the previous call's active set
-    int warm_valid = 0;          // the store holds the masks of a previous call
+    int warm_valid = 0;          // the store holds the masks of a previous call ...
+    int warm_n = 0;              // ... for its first warm_n robots
     int timing = 0;              // record CUDA events around each kernel of a tick
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // the two lane-per-robot class kernels run concurrently: the standing class on the caller's stream, the walking class on
@@ -128,10 +159,19 @@ int setup_variant(Variant& v, int num_sms, int mb) {
     return 0;
 }
 
+void free_lane(LaneVariant& v) {
+    cudaFree(v.d_ws), cudaFree(v.d_defer), cudaFree(v.d_defer_list), cudaFree(v.d_ipm), cudaFree(v.d_ipm_list);
+    v.d_ws = nullptr, v.d_defer = nullptr, v.d_defer_list = nullptr, v.d_ipm = nullptr, v.d_ipm_list = nullptr;
+}
+
 int setup_lane(LaneVariant& v, const DevParams& d, int nf, int num_sms, int ctas_per_sm, int warps, int max_batch) {
     const LaneKernelInfo k = d.h == 30 ? lane_kernel_info_h30(nf, lane_rowmask(d)) : lane_kernel_info_h10(nf, lane_rowmask(d));
     if (!k.fn) return fail("no lane kernel for this horizon");
-    if (v.d_ws) cudaFree(v.d_ws), v.d_ws = nullptr;
+    free_lane(v);
+    v.defer_floats = k.defer_floats;
+    v.defer_cap = std::max(4096, ((max_batch + 3) / 4 + 31) / 32 * 32);  // a quarter of the batch can be parked for the polish (about one robot in eight is)
+    v.ipm_floats = k.ipm_floats;
+    v.ipm_cap = v.defer_cap;                                              // and for the interior point (about one robot in forty is)
     v.fn = k.fn;
     v.threads = 32 * warps;
     v.smem = sizeof(double) * (size_t)k.smem_doubles * 32 * warps;
@@ -145,19 +185,30 @@ int setup_lane(LaneVariant& v, const DevParams& d, int nf, int num_sms, int ctas
     return 0;
 }
 
+// warm-start store: every entry -1 (= no guess for this block) until a tick has written it
+int alloc_ws_mask(bmpc_handle* h, cudaStream_t st) {
+    if (h->ro.ws_mask) return 0;
+    const size_t bytes = (size_t)h->max_batch * h->dp.h * 2 * sizeof(int32_t);
+    CUDA_TRY(cudaMalloc(&h->ro.ws_mask, bytes));
+    CUDA_TRY(cudaMemsetAsync(h->ro.ws_mask, 0xFF, bytes, st));
+    return 0;
+}
+
 int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n > h->max_batch) return fail("batch larger than max_batch given to bmpc_create");
     auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    if (h->warm_enabled && io.ws_mask == nullptr) {  // handle-level warm start (bmpc_warm_start); bmpc_rollout manages its own
-        if (!h->ro.ws_mask) CUDA_TRY(cudaMalloc(&h->ro.ws_mask, (size_t)h->max_batch * h->dp.h * 2 * sizeof(int32_t)));
+    const bool handle_warm = h->warm_enabled && io.ws_mask == nullptr;  // handle-level warm start (bmpc_warm_start); bmpc_rollout manages its own
+    if (handle_warm) {
+        if (alloc_ws_mask(h, st)) return 1;
         io.ws_mask = h->ro.ws_mask;
-        io.warm = h->warm_valid;
-        h->warm_valid = 1;
+        // the store holds the masks of the first warm_n robots of the last call that went through: a larger batch starts cold
+        io.warm = (h->warm_valid && n <= h->warm_n) ? 1 : 0;
+        h->warm_valid = 0;  // (set again below, once every launch of this call has been accepted)
     }
     io.use_tma = aligned16(io.x_fb) && aligned16(io.foot) &&
                  (!io.do_lowlevel || (aligned16(io.q) && aligned16(io.qd) && aligned16(io.pf_w)));
-    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 24 * sizeof(int), st));  // list counts + dynamic work counters
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, 32 * sizeof(int), st));  // list counts + dynamic work counters
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[0], st));
     classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(io.contact, n, h->dp.h, h->max_batch, h->d_lists, h->d_counts);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[1], st));
@@ -183,9 +234,43 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
         // one THREAD per robot (32 robots share every instruction); a class below its size gate is left alone (decided on
         // the device: the kernel returns at once and collect_or_all_kernel passes the whole list on)
         if (!lv.d_ws) CUDA_TRY(cudaMalloc(&lv.d_ws, sizeof(double) * lv.ws_doubles));
-        lv.fn<<<std::min(lv.grid, (n + lv.threads - 1) / lv.threads), lv.threads, lv.smem, ls>>>(
-            h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b, h->d_counts + 12 + b, lv.d_ws, lv.min_count);
+        const int inline_rounds = h->opt_lane_inline_rounds >= 0 ? h->opt_lane_inline_rounds : 1;
+        // h = 10: 9 iterations finish 86 % of the robots (mean 8.5, slowest of a 128-robot CTA 11.6); measured at 262,144 robots:
+        // parking after 8 / 9 / 10 / 11 iterations or never: (store overflows) / 28.6 / 28.9 / 29.4 / 29.8 ms per tick
+        const int ipm_inline = h->opt_lane_ipm_inline >= 0 ? h->opt_lane_ipm_inline : (h->dp.h == 10 ? 9 : 0);
+        LaneDefer df{};
+        if (inline_rounds > 0) {
+            if (!lv.d_defer) CUDA_TRY(cudaMalloc(&lv.d_defer, sizeof(float) * (size_t)lv.defer_floats * lv.defer_cap));
+            if (!lv.d_defer_list) CUDA_TRY(cudaMalloc(&lv.d_defer_list, sizeof(int) * (size_t)lv.defer_cap));
+            // worth further launches from about two waves of slices on (measured: 32,768 robots 6.6 ms in one pass, 6.9 in two; 262,144
+            // robots 33.0 and 29.7 ms)
+            const int two_waves = 2 * lv.grid * lv.threads;
+            df.buf = lv.d_defer, df.list = lv.d_defer_list, df.count = h->d_counts + 20 + b, df.cap = lv.defer_cap;
+            df.inline_rounds = inline_rounds;
+            df.min_count = h->opt_lane_defer_min >= 0 ? h->opt_lane_defer_min : two_waves;
+            if (ipm_inline > 0) {
+                if (!lv.d_ipm) CUDA_TRY(cudaMalloc(&lv.d_ipm, sizeof(float) * (size_t)lv.ipm_floats * lv.ipm_cap));
+                if (!lv.d_ipm_list) CUDA_TRY(cudaMalloc(&lv.d_ipm_list, sizeof(int) * (size_t)lv.ipm_cap));
+                df.ipm_buf = lv.d_ipm, df.ipm_list = lv.d_ipm_list, df.ipm_count = h->d_counts + 24 + b, df.ipm_cap = lv.ipm_cap;
+                df.ipm_inline = ipm_inline;
+            }
+        }
+        const int grid = std::min(lv.grid, (n + lv.threads - 1) / lv.threads);
+        lv.fn<<<grid, lv.threads, lv.smem, ls>>>(h->dp, io, h->d_lists + (size_t)b * h->max_batch, h->d_counts + b, h->d_counts + 12 + b,
+                                                lv.d_ws, lv.min_count, df, 0);
         h->launches += 1;
+        // later passes over the robots the first pass parked, 32 to a warp again: the interior-point stragglers (which may park for
+        // the polish in turn), then the polish stragglers
+        if (df.ipm_buf) {
+            lv.fn<<<std::min(grid, (lv.ipm_cap + lv.threads - 1) / lv.threads), lv.threads, lv.smem, ls>>>(
+                h->dp, io, nullptr, nullptr, h->d_counts + 26 + b, lv.d_ws, 0, df, 2);
+            h->launches += 1;
+        }
+        if (df.buf) {
+            lv.fn<<<std::min(grid, (lv.defer_cap + lv.threads - 1) / lv.threads), lv.threads, lv.smem, ls>>>(
+                h->dp, io, nullptr, nullptr, h->d_counts + 22 + b, lv.d_ws, 0, df, 1);
+            h->launches += 1;
+        }
         return 0;
     };
     auto warp_launch = [&](int b, cudaStream_t ls) -> int {
@@ -245,13 +330,15 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
             int* rlist = h->d_lists + (size_t)(3 + b) * h->max_batch;
             collect_uncertified_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_lists + (size_t)b * h->max_batch, h->d_counts + b, io.status, rlist,
                                                                        h->d_counts + 16 + b);
-            lv.fn<<<std::min(lv.grid, 8), lv.threads, lv.smem, st>>>(last, io, rlist, h->d_counts + 16 + b, h->d_counts + 18 + b, lv.d_ws, 1);
+            lv.fn<<<std::min(lv.grid, 8), lv.threads, lv.smem, st>>>(last, io, rlist, h->d_counts + 16 + b, h->d_counts + 18 + b, lv.d_ws, 1,
+                                                                     LaneDefer{}, 0);
             h->launches += 2;
         }
     }
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev[5], st));
     h->launches += 1;  // classify
     CUDA_TRY(cudaGetLastError());
+    if (handle_warm) h->warm_valid = 1, h->warm_n = n;
     return 0;
 }
 
@@ -263,7 +350,7 @@ int launch_tick(bmpc_handle* h, int n, IoPtrs io, cudaStream_t st) {
 // class and collect_or_all_kernel passes the whole list on.
 int setup_lanes(bmpc_handle* h) {
     for (int b = 0; b < 2; ++b) {
-        if (h->lane[b].d_ws) cudaFree(h->lane[b].d_ws);
+        free_lane(h->lane[b]);
         h->lane[b] = LaneVariant();
     }
     h->lane_min = 0;
@@ -302,7 +389,7 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
     if (e != cudaSuccess || ndev == 0)
         return fail(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail("bmpc_create: device index out of range");
-    CUDA_TRY(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("this build targets sm_100a (Blackwell B200) only");
@@ -373,14 +460,13 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
         rc = setup_variant<10, 10, 6, 32, 6>(h->bucket[0], sms, mb) || setup_variant<10, 20, 6, 128, 1>(h->bucket[1], sms, mb);
     }
     if (rc) {
-        delete h;
+        bmpc_destroy(h);  // frees whatever the variants before the failing one allocated
         return 1;
     }
     e = cudaMalloc(&h->d_lists, sizeof(int) * 5 * (size_t)max_batch);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 24);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, sizeof(int) * 32);
     if (e != cudaSuccess) {
-        cudaFree(h->d_lists);
-        delete h;
+        bmpc_destroy(h);
         return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
     *out = h;
@@ -389,13 +475,13 @@ int bmpc_create(const bmpc_params* params, int device, int max_batch, bmpc_handl
 
 int bmpc_destroy(bmpc_handle* h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    DeviceGuard _guard(h->device);
     cudaFree(h->d_lists);
     cudaFree(h->d_counts);
     for (int b = 0; b < 2; ++b) cudaFree(h->bucket[b].d_scratch);
     cudaFree(h->fallback.d_scratch);
     cudaFree(h->lowlat.d_scratch);
-    cudaFree(h->lane[0].d_ws), cudaFree(h->lane[1].d_ws);
+    free_lane(h->lane[0]), free_lane(h->lane[1]);
     cudaFree(h->ro.contact), cudaFree(h->ro.phase_k), cudaFree(h->ro.t_swing), cudaFree(h->ro.controls);
     cudaFree(h->ro.tau), cudaFree(h->ro.status), cudaFree(h->ro.iters), cudaFree(h->ro.ws_mask);
     for (int i = 0; i < 6; ++i)
@@ -415,7 +501,7 @@ int bmpc_step(bmpc_handle* h, int n, const double* x_fb, const int32_t* phase_k,
     if (!x_fb || !phase_k || !t_swing || !foot || !contact || !q || !qd || !pf_w || !controls || !tau || !status ||
         !iters)
         return fail("bmpc_step: null required pointer");
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     IoPtrs io;
     memset(&io, 0, sizeof(io));
     io.x_fb = x_fb, io.phase_k = phase_k, io.t_swing = t_swing, io.foot = foot, io.contact = contact;
@@ -432,7 +518,7 @@ int bmpc_solve(bmpc_handle* h, int n, const double* x_fb, const int32_t* phase_k
     if (!h) return fail("bmpc_solve: null handle");
     if (!x_fb || !phase_k || !foot || !contact || !controls || !status || !iters)
         return fail("bmpc_solve: null required pointer");
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     IoPtrs io;
     memset(&io, 0, sizeof(io));
     io.x_fb = x_fb, io.phase_k = phase_k, io.foot = foot, io.contact = contact;
@@ -449,7 +535,7 @@ int bmpc_lowlevel(bmpc_handle* h, int n, const double* x_fb, const double* t_swi
     if (!x_fb || !t_swing || !pf_w || !q || !qd || !contact0 || !u0 || !tau)
         return fail("bmpc_lowlevel: null required pointer");
     if (n <= 0) return 0;
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     const int threads = 128, total = 2 * n;
     lowlevel_kernel<<<(total + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         h->dp, n, x_fb, t_swing, pf_w, q, qd, contact0, u0, tau);
@@ -462,7 +548,7 @@ int bmpc_foot_positions(bmpc_handle* h, int n, const double* x_fb, const double*
     if (!h) return fail("bmpc_foot_positions: null handle");
     if (!x_fb || !q || !pf_w) return fail("bmpc_foot_positions: null required pointer");
     if (n <= 0) return 0;
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     const int threads = 128, total = 2 * n;
     foot_positions_kernel<<<(total + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         h->dp, n, x_fb, q, pf_w);
@@ -480,21 +566,20 @@ int bmpc_rollout(bmpc_handle* h, int n, int ticks, double* x, double* foot, int3
     if (n > h->max_batch) return fail("batch larger than max_batch given to bmpc_create");
     if (n_log < 0 || n_log > n) return fail("bmpc_rollout: n_log must be in [0, n]");
     if (n_log > 0 && (!x_log || !foot_log || !u0_log || !tau_log)) return fail("bmpc_rollout: n_log > 0 needs all four log buffers");
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int hz = h->dp.h;
     const size_t nb = (size_t)h->max_batch;
     h->warm_valid = 0;  // the rollout shares the warm-start store: a later warm bmpc_step starts cold
-    if (!h->ro.ws_mask) CUDA_TRY(cudaMalloc(&h->ro.ws_mask, nb * hz * 2 * sizeof(int32_t)));
-    if (!h->ro.contact) {
-        CUDA_TRY(cudaMalloc(&h->ro.contact, nb * hz * 2));
-        CUDA_TRY(cudaMalloc(&h->ro.phase_k, nb * sizeof(int32_t)));
-        CUDA_TRY(cudaMalloc(&h->ro.t_swing, nb * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->ro.controls, nb * hz * 12 * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->ro.tau, nb * 10 * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->ro.status, nb * sizeof(int32_t)));
-        CUDA_TRY(cudaMalloc(&h->ro.iters, nb * sizeof(int32_t)));
-    }
+    if (alloc_ws_mask(h, st)) return 1;
+    // (each buffer on its own: a failed allocation leaves the others in place for the next call and for bmpc_destroy)
+    if (!h->ro.contact) CUDA_TRY(cudaMalloc(&h->ro.contact, nb * hz * 2));
+    if (!h->ro.phase_k) CUDA_TRY(cudaMalloc(&h->ro.phase_k, nb * sizeof(int32_t)));
+    if (!h->ro.t_swing) CUDA_TRY(cudaMalloc(&h->ro.t_swing, nb * sizeof(double)));
+    if (!h->ro.controls) CUDA_TRY(cudaMalloc(&h->ro.controls, nb * hz * 12 * sizeof(double)));
+    if (!h->ro.tau) CUDA_TRY(cudaMalloc(&h->ro.tau, nb * 10 * sizeof(double)));
+    if (!h->ro.status) CUDA_TRY(cudaMalloc(&h->ro.status, nb * sizeof(int32_t)));
+    if (!h->ro.iters) CUDA_TRY(cudaMalloc(&h->ro.iters, nb * sizeof(int32_t)));
     RolloutPtrs r;
     memset(&r, 0, sizeof(r));
     r.x = x, r.foot = foot, r.tick = tick, r.gait = gait, r.q = q;
@@ -544,7 +629,7 @@ int bmpc_debug_assemble(bmpc_handle* h, const double* x_fb, const int32_t* phase
     if (!h) return fail("bmpc_debug_assemble: null handle");
     if (!x_fb || !phase_k || !foot || !contact || !Hc_out || !g_out || !n_out)
         return fail("bmpc_debug_assemble: null required pointer");
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* scratch = nullptr;  // controls + status + iters for the single instance
     const int hz = h->dp.h;
@@ -569,15 +654,19 @@ int bmpc_debug_assemble(bmpc_handle* h, const double* x_fb, const int32_t* phase
 
 int bmpc_set_option(bmpc_handle* h, const char* name, int value) {
     if (!h || !name) return fail("bmpc_set_option: null argument");
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     const std::string k(name);
     if (k == "lane_mode") h->opt_lane_mode = value;
     else if (k == "lane_min") h->opt_lane_min = value;
     else if (k == "lane_ctas_per_sm") h->opt_lane_ctas_per_sm = value;
     else if (k == "lane_warps") h->opt_lane_warps = value;
     else if (k == "lowlat") { h->opt_lowlat = value; return 0; }
+    else if (k == "lane_inline_rounds") { h->opt_lane_inline_rounds = value; return 0; }
+    else if (k == "lane_defer_min") { h->opt_lane_defer_min = value; return 0; }
+    else if (k == "lane_ipm_inline") { h->opt_lane_ipm_inline = value; return 0; }
     else if (k == "lane_prefetch") { h->dp.lane_prefetch = value != 0; return 0; }
     else if (k == "lane_sync") { h->dp.lane_sync = value; return 0; }
+    else if (k == "polish_rounds") { if (value < 1) return fail("bmpc_set_option: polish_rounds must be >= 1"); h->dp.polish_rounds = value; return 0; }
     else return fail("bmpc_set_option: unknown option '" + k + "'");
     CUDA_TRY(cudaDeviceSynchronize());  // the workspace of the lane kernels is re-sized
     return setup_lanes(h);
@@ -587,7 +676,7 @@ int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 
 int bmpc_enable_timing(bmpc_handle* h, int enable) {
     if (!h) return fail("bmpc_enable_timing: null handle");
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     if (enable && !h->ev[0])
         for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     h->timing = enable ? 1 : 0;
@@ -596,7 +685,7 @@ int bmpc_enable_timing(bmpc_handle* h, int enable) {
 
 int bmpc_last_timing(bmpc_handle* h, float* ms5) {
     if (!h || !ms5 || !h->ev[0]) return fail("bmpc_last_timing: timing was not enabled");
-    CUDA_TRY(cudaSetDevice(h->device));
+    ON_DEVICE(h->device);
     CUDA_TRY(cudaEventSynchronize(h->ev[5]));
     for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]));
     return 0;
@@ -604,13 +693,22 @@ int bmpc_last_timing(bmpc_handle* h, float* ms5) {
 
 int bmpc_measure_fma_peak(int device, int fp64, double* tflops_out) {
     if (!tflops_out) return fail("bmpc_measure_fma_peak: null output");
-    CUDA_TRY(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
-    void* buf = nullptr;
+    struct Scratch {  // released on every return path
+        void* buf = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Scratch() {
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            cudaFree(buf);
+        }
+    } sc;
+    void*& buf = sc.buf;
+    cudaEvent_t &e0 = sc.e0, &e1 = sc.e1;
     CUDA_TRY(cudaMalloc(&buf, sizeof(double) * threads * (size_t)blocks));
-    cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
     double best = 0.0;
@@ -627,9 +725,6 @@ int bmpc_measure_fma_peak(int device, int fp64, double* tflops_out) {
         const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
         if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(buf);
     CUDA_TRY(cudaGetLastError());
     *tflops_out = best;
     return 0;

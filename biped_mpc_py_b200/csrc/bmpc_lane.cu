@@ -12,7 +12,7 @@ static LaneKernelInfo pick(unsigned rowmask) {
     LaneKernel fn = lane_tick_kernel<HZ, NF, 0u>;
     if (rowmask == kRowsRef) fn = lane_tick_kernel<HZ, NF, kRowsRef>;
     else if (rowmask == kRowsSym) fn = lane_tick_kernel<HZ, NF, kRowsSym>;
-    return {fn, LaneRec<HZ, NF>::total, LaneRec<HZ, NF>::smem_doubles};
+    return {fn, LaneRec<HZ, NF>::total, LaneRec<HZ, NF>::smem_doubles, LaneRec<HZ, NF>::defer_floats, LaneRec<HZ, NF>::ipm_floats};
 }
 
 #if !defined(BMPC_LANE_UNIT) || BMPC_LANE_UNIT == 10

@@ -27,6 +27,7 @@
 // A robot this path does not certify keeps status 1 and is re-solved by the warp-per-robot kernels (bmpc.cu).
 #pragma once
 #include "bmpc_kernels.cuh"
+#include "bmpc_lane_api.h"
 #include "bmpc_polish.cuh"
 
 namespace bmpc {
@@ -53,6 +54,14 @@ namespace bmpc {
 #define BMPC_CBAR() asm volatile("" ::: "memory")
 #else
 #define BMPC_CBAR()
+#endif
+
+// LaneSolver::run is forced inline in the kernels (see there); the host test build leaves the decision to the compiler (forced,
+// gcc needs a quarter of an hour for the twelve instantiations)
+#ifdef BMPC_LANE_HOST_ONLY
+#define BMPC_RUN_INLINE
+#else
+#define BMPC_RUN_INLINE __forceinline__
 #endif
 
 struct SV {  // strided view of one lane's slice of a lane-interleaved array
@@ -108,6 +117,8 @@ struct LaneRec {  // per-block record, in doubles
     static constexpr int REC = 164;
     static constexpr int total = S * REC;
     static constexpr int smem_doubles = 78;   // per lane: packed cost-to-go
+    static constexpr int defer_floats = S * (NR + 1) + 4;  // parked robot (LaneDefer), polish store: per block the active-row mask and NR multipliers; gs, rdmax, iterations
+    static constexpr int ipm_floats = S * (5 + 2 * NR) + 4;  // interior-point store: per block u, NR slacks, NR multipliers; gs, iterations
 };
 
 // F32: the interior point stores its stage factors (Y, L) as float (the Riccati recursion itself, the cost-to-go and the
@@ -130,8 +141,20 @@ struct LaneSolver {
     double ln[2][LB], lnb[2];  // the two line-foot rows in block coordinates and their right-hand sides
     unsigned footbits, rowmask;
     double dt, vm;
+    // later passes (bmpc_lane_api.h); mode: 0 first pass, 1 polish pass, 2 interior-point pass; park: this pass parks its stragglers.
+    // (A reference to the kernel parameter, like p: read from the constant bank where it is used instead of living in registers.)
+    const LaneDefer& df;
+    int mode = 0;
+    bool park = false;
 
-    BMPC_HD LaneSolver(const DevParams& pp, SV w, SV ps, int lane) : p(pp), ws(w), Ps(ps), lane_id(lane) {}
+    BMPC_HD LaneSolver(const DevParams& pp, SV w, SV ps, int lane, const LaneDefer& d) : p(pp), ws(w), Ps(ps), lane_id(lane), df(d) {}
+    // element e of parked-robot record q
+    BMPC_HD __forceinline__ float& parked(int q, int e) const {
+        return df.buf[((size_t)(q / 32) * L::defer_floats + e) * 32 + (q % 32)];
+    }
+    BMPC_HD __forceinline__ float& parked_ipm(int q, int e) const {
+        return df.ipm_buf[((size_t)(q / 32) * L::ipm_floats + e) * 32 + (q % 32)];
+    }
 
     // Bulk prefetch into L2 of the first `ndoubles` entries of block record v of this warp's 32 robots (one contiguous
     // ndoubles x 256-byte panel): issued one stage ahead, so that the sweeps find their operands in L2 instead of paying the
@@ -146,14 +169,61 @@ struct LaneSolver {
     }
     static constexpr int kFacDoubles = F32 ? 38 : 75;  // extent of the stored stage factor, in doubles
 
-    // stage factor storage: element i of [Y (60) | L (15)] of record r
-    template <bool F> BMPC_HD __forceinline__ void st_fac(SV r, int i, double x) const {
-        if constexpr (F) (reinterpret_cast<float*>(r.p + (size_t)L::o_Y * BMPC_LS) - lane_id)[(size_t)i * BMPC_LS] = (float)x;
-        else r[L::o_Y + i] = x;
+    // stage factor storage: [Y (5 rows of 12) | L (15)] of record r.  As float the 76 values (one of padding) are 19 groups of four,
+    // group g of lane l at float4 index g * 32 + l of the record's factor region: one 16-byte access per lane and group (a warp
+    // moves 512 contiguous bytes per instruction) instead of four 4-byte ones - the sweeps are bound by the number of memory
+    // instructions they issue, not by the bytes.  As double (polish) element i sits at o_Y + i like everything else.
+    struct alignas(16) F4 {
+        float x, y, z, w;
+    };
+    BMPC_HD __forceinline__ F4* fac4(SV r, int g) const {
+        return reinterpret_cast<F4*>(r.p + (size_t)L::o_Y * BMPC_LS - lane_id) + ((size_t)g * BMPC_LS + lane_id);
     }
-    template <bool F> BMPC_HD __forceinline__ double ld_fac(SV r, int i) const {
-        if constexpr (F) return (double)(reinterpret_cast<const float*>(r.p + (size_t)L::o_Y * BMPC_LS) - lane_id)[(size_t)i * BMPC_LS];
-        else return r[L::o_Y + i];
+    // row a of Y (12 values)
+    template <bool F> BMPC_HD __forceinline__ void st_fac_row(SV r, int a, const double (&y)[12]) const {
+        if constexpr (F) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) *fac4(r, a * 3 + q) = F4{(float)y[4 * q], (float)y[4 * q + 1], (float)y[4 * q + 2], (float)y[4 * q + 3]};
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) r[L::o_Y + a * 12 + j] = y[j];
+        }
+    }
+    template <bool F> BMPC_HD __forceinline__ void ld_fac_row(SV r, int a, double (&y)[12]) const {
+        if constexpr (F) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const F4 t = *fac4(r, a * 3 + q);
+                y[4 * q] = (double)t.x, y[4 * q + 1] = (double)t.y, y[4 * q + 2] = (double)t.z, y[4 * q + 3] = (double)t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) y[j] = r[L::o_Y + a * 12 + j];
+        }
+    }
+    // the packed Cholesky factor (15 values, reciprocal diagonal)
+    template <bool F> BMPC_HD __forceinline__ void st_fac_L(SV r, const double (&Lc)[15]) const {
+        if constexpr (F) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *fac4(r, 15 + q) = F4{(float)Lc[4 * q], (float)Lc[4 * q + 1], (float)Lc[4 * q + 2], q < 3 ? (float)Lc[4 * q + 3] : 0.f};
+        } else {
+#pragma unroll
+            for (int e = 0; e < 15; ++e) r[L::o_Y + 60 + e] = Lc[e];
+        }
+    }
+    template <bool F> BMPC_HD __forceinline__ void ld_fac_L(SV r, double (&Lc)[15]) const {
+        if constexpr (F) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const F4 t = *fac4(r, 15 + q);
+                Lc[4 * q] = (double)t.x, Lc[4 * q + 1] = (double)t.y, Lc[4 * q + 2] = (double)t.z;
+                if (q < 3) Lc[4 * q + 3] = (double)t.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 15; ++e) Lc[e] = r[L::o_Y + 60 + e];
+        }
     }
 
     static BMPC_HD __forceinline__ constexpr int pk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
@@ -491,10 +561,14 @@ struct LaneSolver {
                 }
             }
         if (!ok) return false;
+        {
+            double Lc[15];
 #pragma unroll
-        for (int a = 0; a < LB; ++a)
+            for (int a = 0; a < LB; ++a)
 #pragma unroll
-            for (int k = 0; k <= a; ++k) st_fac<FS>(r, 60 + tri(a, k), Lr[a][k]);
+                for (int k = 0; k <= a; ++k) Lc[tri(a, k)] = Lr[a][k];
+            st_fac_L<FS>(r, Lc);
+        }
         // backward half of the solve: w = inv(L) (B' pv - rhs)
         double w[LB];
         {
@@ -580,14 +654,16 @@ struct LaneSolver {
         }
         At_mul(r9, dte, pv);
 #pragma unroll
-        for (int j = 0; j < 6; ++j)
+        for (int a = 0; a < LB; ++a) {
+            double y[12];
 #pragma unroll
-            for (int a = 0; a < LB; ++a) {
-                st_fac<FS>(r, a * 12 + j, hi[j][a]);
-                st_fac<FS>(r, a * 12 + 6 + j, lo[j][a]);
+            for (int j = 0; j < 6; ++j) {
+                y[j] = hi[j][a], y[6 + j] = lo[j][a];
                 pv[j] -= hi[j][a] * w[a];
                 pv[6 + j] -= lo[j][a] * w[a];
             }
+            st_fac_row<FS>(r, a, y);
+        }
         if (last) return true;
         BMPC_CBAR();
         // cost-to-go of the previous state: A' P A (+ Q)
@@ -613,10 +689,10 @@ struct LaneSolver {
                                                   const double (&N)[LB * LB], int dim) {
         constexpr bool FS = F32 && !POL;
         const double dte = dyn_of(v) ? dt : 0.0;
-        double B3[3][LB], g5[LB], w[LB], Lc[15];
+        double B3[3][LB], g5[LB], w[LB], Lc[15], r9[9];
         load_B3(r, B3);
-#pragma unroll
-        for (int e = 0; e < 15; ++e) Lc[e] = ld_fac<FS>(r, 60 + e);
+        load_r9(r, dte, r9);
+        ld_fac_L<FS>(r, Lc);
         Bt_mul(B3, pv + 6, g5);
         if constexpr (POL) Nt_mul(N, dim, g5);
 #pragma unroll
@@ -625,15 +701,18 @@ struct LaneSolver {
 #pragma unroll
             for (int k = 0; k < c; ++k) g -= Lc[tri(c, k)] * w[k];
             w[c] = g * Lc[tri(c, c)];
-            r[ow + c] = w[c];
         }
-        double r9[9];
-        load_r9(r, dte, r9);
         At_mul(r9, dte, pv);
 #pragma unroll
-        for (int a = 0; a < LB; ++a)
+        for (int a = 0; a < LB; ++a) {
+            double y[12];
+            ld_fac_row<FS>(r, a, y);
 #pragma unroll
-            for (int j = 0; j < 12; ++j) pv[j] -= ld_fac<FS>(r, a * 12 + j) * w[a];
+            for (int j = 0; j < 12; ++j) pv[j] -= y[j] * w[a];
+        }
+        // (stored last: a store in the middle would pin the factor loads behind it)
+#pragma unroll
+        for (int c = 0; c < LB; ++c) r[ow + c] = w[c];
     }
 
     // forward half of a solve (one stage): x = -inv(L') (w + Y z); z <- A z + B x (POL: B N x).  Returns x.
@@ -641,13 +720,13 @@ struct LaneSolver {
     BMPC_HD __forceinline__ void solve_fwd_stage(int v, SV r, int ow, double (&z)[12], double (&xs)[LB]) const {
         constexpr bool FS = F32 && !POL;
         double t[LB], Lc[15];
-#pragma unroll
-        for (int e = 0; e < 15; ++e) Lc[e] = ld_fac<FS>(r, 60 + e);
+        ld_fac_L<FS>(r, Lc);
 #pragma unroll
         for (int a = 0; a < LB; ++a) {
-            double x = r[ow + a];
+            double x = r[ow + a], y[12];
+            ld_fac_row<FS>(r, a, y);
 #pragma unroll
-            for (int j = 0; j < 12; ++j) x += ld_fac<FS>(r, a * 12 + j) * z[j];
+            for (int j = 0; j < 12; ++j) x += y[j] * z[j];
             t[a] = x;
         }
 #pragma unroll
@@ -665,6 +744,13 @@ struct LaneSolver {
         double B3[3][LB], r9[9];
         load_B3(r, B3);
         load_r9(r, dte, r9);
+        A_mul(r9, dte, z);
+        B_mul_add(B3, ustep, z + 6);
+    }
+    // the same with the stage's maps loaded by the caller (at the top of the stage, so that their latency overlaps the solve: the
+    // compiler cannot move these loads above the stores of the stage itself)
+    BMPC_HD __forceinline__ void advance_z(const double (&B3)[3][LB], const double (&r9)[9], double dte, const double (&ustep)[LB],
+                                           double (&z)[12]) const {
         A_mul(r9, dte, z);
         B_mul_add(B3, ustep, z + 6);
     }
@@ -827,9 +913,11 @@ struct LaneSolver {
         return x;
 #endif
     }
-    BMPC_HD __forceinline__ void stage_sync() const {
+    // (p.lane_sync & 8: a barrier only before the first stage of a sweep - the warps of a CTA then run the same sweep, i.e. the
+    //  same loop body, without waiting for each other at every stage)
+    BMPC_HD __forceinline__ void stage_sync(bool first) const {
 #ifdef __CUDA_ARCH__
-        if ((p.lane_sync & 3) >= 2) __syncthreads();
+        if ((p.lane_sync & 3) >= 2 && (first || !(p.lane_sync & 8))) __syncthreads();
 #endif
     }
     // the polish: in lockstep like the interior point, or (p.lane_sync & 4) every warp on its own - the number of polish rounds
@@ -842,14 +930,17 @@ struct LaneSolver {
         return x;
 #endif
     }
-    BMPC_HD __forceinline__ void stage_sync_polish() const {
+    BMPC_HD __forceinline__ void stage_sync_polish(bool first) const {
 #ifdef __CUDA_ARCH__
-        if ((p.lane_sync & 3) >= 2 && !(p.lane_sync & 4)) __syncthreads();
+        if ((p.lane_sync & 3) >= 2 && !(p.lane_sync & 4) && (first || !(p.lane_sync & 8))) __syncthreads();
 #endif
     }
 
-    // ---- the whole tick; inst < 0: no robot for this lane (it only takes part in the group's barriers) ------------------
-    BMPC_HD void run(const IoPtrs& io, int inst) {
+    // ---- the whole tick; inst < 0: no robot for this lane (it only takes part in the group's barriers); q: position of the
+    //      robot among the parked ones (second pass only) ----------------------------------------------------------------
+    //      (forced inline: as a real call the solver object - line-foot rows, pointers, scalars read in every row pass - lives
+    //      in local memory; the compiler's own heuristic stops inlining a function of this size: measured +30 % kernel time)
+    BMPC_HD BMPC_RUN_INLINE void run(const IoPtrs& io, int inst, int q = -1) {
         BMPC_ASSUME_SPACES();
         dt = p.dt;
         vm = dt / p.mass;
@@ -980,7 +1071,36 @@ struct LaneSolver {
             }
 
             // ---- 2. interior point: start ----
-            if (act) {
+            if (act && mode == 2) {
+                // interior-point pass: the parked interior point; its stationarity residual rd = Hc u + g + C' lam is recomputed
+                constexpr int PB = 5 + 2 * NR;
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) r[L::o_u + c] = (double)parked_ipm(q, v * PB + c);
+                    for_rows([&](auto, int slot, int) {
+                        r[L::o_s + slot] = (double)parked_ipm(q, v * PB + 5 + slot);
+                        r[L::o_l + slot] = (double)parked_ipm(q, v * PB + 5 + NR + slot);
+                    });
+                }
+                gs = (double)parked_ipm(q, S * PB);
+                grad(L::o_u, L::o_tv, nullptr);
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+                    double acc[LB];
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) acc[c] = r[L::o_tv + c];
+                    for_rows([&](auto tag, int slot, int) { radd(tag, acc, r[L::o_l + slot]); });
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) {
+                        r[L::o_rd + c] = acc[c];
+                        rdmax = fmax(rdmax, fabs(acc[c]));
+                    }
+                }
+            }
+            if (act && mode == 0) {
                 // g = gradient at u = 0 (scale of the problem)
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
@@ -1038,7 +1158,8 @@ struct LaneSolver {
         int status = 1, it = 0;
         double alpha = 0.0, tgt = 0.0;
         const double dummyN[LB * LB] = {0.0};  // (unused: the interior point works on the inputs themselves)
-        bool ipm = act;
+        bool ipm = act && mode != 1, park_ipm = false;
+        if (ipm && mode == 2) it = (int)parked_ipm(q, S * (5 + 2 * NR) + 1);
 #pragma unroll 1
         while (group_any(ipm)) {
             if (ipm && it >= p.max_iter) status = 1, ipm = false;
@@ -1054,7 +1175,7 @@ struct LaneSolver {
             }
 #pragma unroll 1
             for (int v = S - 1; v >= 0; --v) {
-                stage_sync();
+                stage_sync(v == S - 1);
                 if (!ipm) continue;
                 prefetch_rec(v - 1, L::o_Y);
                 SV r = rec(v);
@@ -1086,7 +1207,7 @@ struct LaneSolver {
                 for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
-                    stage_sync();
+                    stage_sync(v == 0);
                     if (!ipm) continue;
                     prefetch_rec(v + 1, L::o_Y + kFacDoubles);
                     SV r = rec(v);
@@ -1094,10 +1215,14 @@ struct LaneSolver {
                     load_rows(r, sv, lv);
 #pragma unroll
                     for (int c = 0; c < LB; ++c) u[c] = r[L::o_u + c];
+                    const double dte = dyn_of(v) ? dt : 0.0;
+                    double B3[3][LB], r9[9];
+                    load_B3(r, B3);
+                    load_r9(r, dte, r9);
                     solve_fwd_stage<false>(v, r, L::o_xv, z, xs);
 #pragma unroll
                     for (int c = 0; c < LB; ++c) r[L::o_xv + c] = xs[c];
-                    advance_z(v, r, xs, z);
+                    advance_z(B3, r9, dte, xs, z);
                     for_rows([&](auto tag, int slot, int) {
                         const double s = sv[slot], lm = lv[slot];
                         const RowStep q = row_affine(rdot(tag, u), rdot(tag, xs), s, lm, rrhs(tag));
@@ -1118,7 +1243,7 @@ struct LaneSolver {
             // -- sweep C (backward): corrector right-hand side C' wc, wc = (dsa dla - sigma mu) / s, backward half of its solve
 #pragma unroll 1
             for (int v = S - 1; v >= 0; --v) {
-                stage_sync();
+                stage_sync(v == S - 1);
                 if (!ipm) continue;
                 prefetch_rec(v - 1, L::o_Y + kFacDoubles);
                 SV r = rec(v);
@@ -1146,7 +1271,7 @@ struct LaneSolver {
                 for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
-                    stage_sync();
+                    stage_sync(v == 0);
                     if (!ipm) continue;
                     prefetch_rec(v + 1, L::o_Y + kFacDoubles);
                     SV r = rec(v);
@@ -1157,8 +1282,12 @@ struct LaneSolver {
                         u[c] = r[L::o_u + c];
                         x5[c] = r[L::o_xv + c];
                     }
+                    const double dte = dyn_of(v) ? dt : 0.0;
+                    double B3[3][LB], r9[9];
+                    load_B3(r, B3);
+                    load_r9(r, dte, r9);
                     solve_fwd_stage<false>(v, r, L::o_du, z, xs);
-                    advance_z(v, r, xs, z);
+                    advance_z(B3, r9, dte, xs, z);
 #pragma unroll
                     for (int c = 0; c < LB; ++c) {
                         d5[c] = xs[c] + x5[c];
@@ -1191,11 +1320,67 @@ struct LaneSolver {
                     }
                 }
             }
+            // first pass: a robot that has not converged after ipm_inline iterations leaves the loop here and is parked below
+            // (while the store has room: a robot that finds it full simply carries on in this pass)
+            if (ipm && mode == 0 && park && df.ipm_buf && it >= df.ipm_inline && *(volatile const int*)df.ipm_count < df.ipm_cap)
+                ipm = false, park_ipm = true;
+        }
+        // parked for the interior-point pass: the step just computed is applied (as the next sweep A would have) and the new
+        // interior point (u, s, lam) stored
+        if (park_ipm) {
+            int qq;
+#ifdef __CUDA_ARCH__
+            qq = atomicAdd(df.ipm_count, 1);
+#else
+            qq = (*df.ipm_count)++;
+#endif
+            if (qq < df.ipm_cap) {
+                constexpr int PB = 5 + 2 * NR;
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+                    double u[LB], x5[LB], d5[LB];
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) u[c] = r[L::o_u + c], x5[c] = r[L::o_xv + c], d5[c] = r[L::o_du + c];
+                    for_rows([&](auto tag, int slot, int) {
+                        const double s = r[L::o_s + slot], lm = r[L::o_l + slot];
+                        const RowStep qr = row_affine(rdot(tag, u), rdot(tag, x5), s, lm, rrhs(tag));
+                        const double wc = (qr.dsa * qr.dla - tgt) * qr.is;
+                        const double ds = -qr.rp - rdot(tag, d5), dl = -lm - wc - qr.d * ds;
+                        parked_ipm(qq, v * PB + 5 + slot) = (float)(s + alpha * ds);
+                        parked_ipm(qq, v * PB + 5 + NR + slot) = (float)(lm + alpha * dl);
+                    });
+#pragma unroll
+                    for (int c = 0; c < LB; ++c) parked_ipm(qq, v * PB + c) = (float)(u[c] + alpha * d5[c]);
+                }
+                parked_ipm(qq, S * PB) = (float)gs;
+                parked_ipm(qq, S * PB + 1) = (float)it;
+                df.ipm_list[qq] = inst;  // (status stays 1 until a later pass certifies the robot)
+            } else {
+                status = 1;  // lost the race for the last places of the store: the warp-per-robot kernels take the robot
+            }
         }
 
         // ---- 3. active-set polish + certificate (one attempt; anything else goes to the warp-per-robot kernels) ----
-        bool pol = act && status == 0, polished = false;
-        if (pol) {
+        bool pol = act && status == 0, polished = false, park_pol = false;
+        int round = 0;
+        if (mode == 1) {
+            // polish pass: the parked state instead of an interior-point iterate
+            pol = act;
+            if (pol) {
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+                    r[L::o_am] = (double)parked(q, v * (NR + 1));
+                    for_rows([&](auto, int slot, int) { r[L::o_l + slot] = (double)parked(q, v * (NR + 1) + 1 + slot); });
+                }
+                gs = (double)parked(q, S * (NR + 1));
+                rdmax = (double)parked(q, S * (NR + 1) + 1);
+                it = (int)parked(q, S * (NR + 1) + 2);
+                status = 1;
+            }
+            round = df.inline_rounds;
+        } else if (pol) {
             // diag(Hc) from the uncontrolled cost-to-go (into tv)
             init_P();
 #pragma unroll 1
@@ -1254,7 +1439,6 @@ struct LaneSolver {
             }
             status = 1;
         }
-        int round = 0;
 #pragma unroll 1
         while (group_any_polish(pol)) {
             if (pol && round >= (HZ > 10 ? 3 : 1) * p.polish_rounds) pol = false;  // (long horizons: more weakly active rows to walk through)
@@ -1281,7 +1465,7 @@ struct LaneSolver {
             }
 #pragma unroll 1
             for (int v = S - 1; v >= 0; --v) {
-                stage_sync_polish();
+                stage_sync_polish(v == S - 1);
                 if (!pol) continue;
                 prefetch_rec(v - 1, L::REC);
                 SV r = rec(v);
@@ -1311,7 +1495,7 @@ struct LaneSolver {
                 for (int a = 0; a < 12; ++a) z[a] = 0.0;
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
-                    stage_sync_polish();
+                    stage_sync_polish(v == 0);
                     if (!pol) continue;
                     prefetch_rec(v + 1, L::REC);
                     SV r = rec(v);
@@ -1368,6 +1552,30 @@ struct LaneSolver {
                 if (fail) pol = false;
                 else if (!changed) polished = true, pol = false;
             }
+            // a robot that needs more rounds than this pass runs leaves the loop here and is parked below
+            if (pol && mode != 1 && park && df.buf && round >= df.inline_rounds && *(volatile const int*)df.count < df.cap)
+                pol = false, park_pol = true;
+        }
+        // parked for the polish pass: active-row masks and multipliers of every block
+        if (park_pol) {
+            int qq;
+#ifdef __CUDA_ARCH__
+            qq = atomicAdd(df.count, 1);
+#else
+            qq = (*df.count)++;
+#endif
+            if (qq < df.cap) {
+#pragma unroll 1
+                for (int v = 0; v < S; ++v) {
+                    SV r = rec(v);
+                    parked(qq, v * (NR + 1)) = (float)r[L::o_am];
+                    for_rows([&](auto, int slot, int) { parked(qq, v * (NR + 1) + 1 + slot) = (float)r[L::o_l + slot]; });
+                }
+                parked(qq, S * (NR + 1)) = (float)gs;
+                parked(qq, S * (NR + 1) + 1) = (float)rdmax;
+                parked(qq, S * (NR + 1) + 2) = (float)it;
+                df.list[qq] = inst;  // (status 1 until the polish pass certifies the robot)
+            }                        // (store full: status 1, the warp-per-robot kernels take the robot)
         }
         if (act && !polished) {
             io.status[inst] = 1;
@@ -1465,15 +1673,19 @@ struct LaneSolver {
 template <int HZ, int NF, unsigned RM>
 __global__ void __launch_bounds__(256, 1) lane_tick_kernel(const __grid_constant__ DevParams p, const IoPtrs io,
                                                            const int* __restrict__ work_list, const int* __restrict__ work_count,
-                                                           int* __restrict__ slice_counter, double* __restrict__ wsbase, int min_count) {
+                                                           int* __restrict__ slice_counter, double* __restrict__ wsbase, int min_count,
+                                                           const __grid_constant__ LaneDefer df, int mode) {
     using L = LaneRec<HZ, NF>;
     extern __shared__ double lane_smem[];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int warp = blockIdx.x * nw + wib;
-    const int count = *work_count;
+    // modes 1 and 2 (later passes): the work list is the list of the robots parked for that pass
+    const int count = mode == 1 ? min(*df.count, df.cap) : mode == 2 ? min(*df.ipm_count, df.ipm_cap) : *work_count;
+    if (mode == 1) work_list = df.list;
+    if (mode == 2) work_list = df.ipm_list;
     // a class too small to be worth 32-robot slices stays on the warp-per-robot kernel: collect_or_all_kernel hands the whole list over
-    if (count < min_count) return;
+    if (mode == 0 && count < min_count) return;
     SV ws{wsbase + (size_t)warp * L::total * 32 + lane};
     SV ps{lane_smem + (size_t)wib * L::smem_doubles * 32 + lane};
     while (true) {
@@ -1489,8 +1701,10 @@ __global__ void __launch_bounds__(256, 1) lane_tick_kernel(const __grid_constant
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= count) break;
         }
-        LaneSolver<HZ, NF, true, RM> solver(p, ws, ps, lane);
-        solver.run(io, base + lane < count ? work_list[base + lane] : -1);
+        LaneSolver<HZ, NF, true, RM> solver(p, ws, ps, lane, df);
+        solver.mode = mode;
+        solver.park = mode == 2 || (mode == 0 && count >= df.min_count);
+        solver.run(io, base + lane < count ? work_list[base + lane] : -1, base + lane);
         __syncwarp();
     }
 }

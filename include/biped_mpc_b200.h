@@ -148,8 +148,19 @@ int bmpc_debug_assemble(bmpc_handle* h,
  *   "lane_warps"        warps (32 robots each) per CTA of the lane-per-robot kernels (default 4)
  *   "lane_prefetch"     0 disables the bulk L2 prefetch of the lane-per-robot kernels (measurement only)
  *   "lane_sync"         lockstep of the warps of a lane-kernel CTA: 2 (default) barrier per stage of every sweep,
- *                       1 per iteration, 0 independent warps (measurement only)
+ *                       1 per iteration, 0 independent warps; + 4: the polish of every warp on its own; + 8: one barrier
+ *                       per sweep instead of per stage (measurement only: all measured slower than the default)
+ *   "lane_ipm_inline"   interior-point iterations of the lane kernels' first pass before a robot that has not converged
+ *                       is parked for the interior-point pass (default 9 at h = 10, 0 = never at h = 30)
+ *   "lane_inline_rounds" polish rounds of the first pass before a robot that needs more is parked for the polish pass
+ *                       (default 1; 0: no later passes at all)
+ *   "lane_defer_min"    smallest class for which robots are parked (default: two waves of resident slices; -1 restores it)
+ *   "polish_rounds"     budget of polish rounds per attempt (default 4 at h = 10, 16 at h = 30)
  *   "lowlat"            0 disables the 128-thread low-latency kernel used for batches <= 8
+ * With "lane_min" = 1, "lane_defer_min" = 1 and "lowlat" = 0 every robot takes the same code path whatever batch it
+ * arrives in: results are bit-identical for any sharding of the robots over calls or GPUs ("lane_mode" = 0 with
+ * "lowlat" = 0 does the same with the warp-per-robot kernels); with the default size gates the kernel family, and with it
+ * the last bits of a result, depend on the batch.
  * Synchronises the device (the lane workspace is re-sized). */
 int bmpc_set_option(bmpc_handle* h, const char* name, int value);
 
@@ -157,8 +168,8 @@ int bmpc_set_option(bmpc_handle* h, const char* name, int value);
 int64_t bmpc_launch_count(const bmpc_handle* h);
 
 /* Per-kernel device timing of the last bmpc_step/bmpc_solve (CUDA events on the launching
- * stream): ms5 = {classify, lane-per-robot kernel of the walking class, lane-per-robot kernel of the
- * standing class (each 0 when the batch is below the size gates), walking-class warp-per-robot kernel
+ * stream): ms5 = {classify, lane-per-robot kernels of the walking class (first pass + interior-point pass + polish
+ * pass), lane-per-robot kernels of the standing class (each 0 when the batch is below the size gates), walking-class warp-per-robot kernel
  * (<= h stance foot-stages; after a lane launch: the collect step + what that did not certify),
  * standing-class warp-per-robot kernel (+ the h = 30 dense re-solve)}.  While timing is enabled the
  * kernels of a tick run one after the other (normally the two classes run concurrently on two

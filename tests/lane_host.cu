@@ -9,10 +9,48 @@
 
 using namespace bmpc;
 
+// two_pass: the first call parks the stragglers (LaneDefer, bmpc_lane_api.h: a robot whose interior point has not converged
+// after g_ipm_inline iterations, a robot that needs more than one polish round) and later calls continue from the parked
+// records, as the launches of the GPU dispatch do
+static int g_two_pass = 0, g_parked = 0, g_parked_ipm = 0, g_ipm_inline = 9;
+extern "C" void lane_host_set_two_pass(int on, int ipm_inline) { g_two_pass = on, g_ipm_inline = ipm_inline; }
+extern "C" int lane_host_parked(void) { return g_parked; }
+extern "C" int lane_host_parked_ipm(void) { return g_parked_ipm; }
+
+template <int HZ, int NF, bool F32, unsigned RM>
+static void run_f(const DevParams& d, std::vector<double>& w, std::vector<double>& ps, const IoPtrs& io, int i) {
+    if (!g_two_pass) {
+        const LaneDefer none{};
+        LaneSolver<HZ, NF, F32, RM>(d, SV{w.data()}, SV{ps.data()}, 0, none).run(io, i);
+        return;
+    }
+    // one parked record per store; on the host the lane interleave is 1, but the record layout keeps its 32-wide stride
+    std::vector<float> buf((size_t)LaneRec<HZ, NF>::defer_floats * 32, 0.f), ibuf((size_t)LaneRec<HZ, NF>::ipm_floats * 32, 0.f);
+    int list[32] = {0}, count = 0, ilist[32] = {0}, icount = 0;
+    const LaneDefer df{buf.data(), list, &count, 32, 1, 0, ibuf.data(), ilist, &icount, 32, g_ipm_inline};
+    LaneSolver<HZ, NF, F32, RM> first(d, SV{w.data()}, SV{ps.data()}, 0, df);
+    first.park = true;
+    first.run(io, i);
+    if (icount) {
+        g_parked_ipm += 1;
+        for (auto& x : w) x = -7.0;  // a later pass must not depend on anything an earlier one left in the workspace
+        LaneSolver<HZ, NF, F32, RM> second(d, SV{w.data()}, SV{ps.data()}, 0, df);
+        second.mode = 2;
+        second.park = true;
+        second.run(io, ilist[0], 0);
+    }
+    if (count) {
+        g_parked += 1;
+        for (auto& x : w) x = -7.0;
+        LaneSolver<HZ, NF, F32, RM> third(d, SV{w.data()}, SV{ps.data()}, 0, df);
+        third.mode = 1;
+        third.run(io, list[0], 0);
+    }
+}
 template <int HZ, int NF, unsigned RM>
 static void run_rm(const DevParams& d, std::vector<double>& w, std::vector<double>& ps, const IoPtrs& io, int i, bool f32) {
-    if (f32) LaneSolver<HZ, NF, true, RM>(d, SV{w.data()}, SV{ps.data()}, 0).run(io, i);
-    else LaneSolver<HZ, NF, false, RM>(d, SV{w.data()}, SV{ps.data()}, 0).run(io, i);
+    if (f32) run_f<HZ, NF, true, RM>(d, w, ps, io, i);
+    else run_f<HZ, NF, false, RM>(d, w, ps, io, i);
 }
 // same choice as bmpc_lane.cu: the instantiation specialised for the presolve's row set if there is one, else the generic one
 template <int HZ, int NF>

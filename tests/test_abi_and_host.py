@@ -86,3 +86,13 @@ def test_gait_mirror_follows_reference_float_phase():
         assert int(gait_phase(np.array([t]), mpc)[0]) == rm.gait_phase(t, rm.MPCParams())
         assert np.array_equal(get_contact_sequence(t, mpc), rm.get_contact_sequence(t, rm.MPCParams()))
     assert int((3 * 0.04) // 0.04) == 2  # the quirk itself (MPC.py:56)
+
+
+def test_synthetic_workload_feet_match_the_oracle_kinematics():
+    """The synthetic workload's foot positions (biped_mpc_py_b200/synth.py, a vectorised host mirror of getFootPositionWorld,
+    MPC.py:406-424) against the oracle, pose by pose: the bench and the property tests start from the reference's kinematics."""
+    from biped_mpc_py_b200 import synth
+    from oracle import reference_mpc as rm
+    b = synth.make_batch(200, shard_index=3)
+    want = np.stack([rm.getFootPositionWorld(b["x_fb"][i], b["q"][i], rm.BipedParams()).reshape(6) for i in range(200)])
+    np.testing.assert_allclose(b["pf_w"], want, rtol=0, atol=1e-13)

@@ -149,3 +149,37 @@ def test_lane_solver_horizon_30(lane_lib):
     for i in picks:
         _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, biped, b["contact"][i], extend=True)
         assert np.abs(out["controls"][i] - u).max() / max(1.0, np.abs(u).max()) <= 1e-5, i
+
+
+@pytest.mark.parametrize("h", [10, 30])
+def test_lane_solver_later_passes_match_one_pass(lane_lib, h):
+    """The later passes of the GPU dispatch (bmpc_lane_api.h) on the host: a robot whose interior point has not converged after
+    a set number of iterations is parked (interior point as float) and continued by a second launch, a robot that needs more
+    than one polish round is parked with its active-row masks and multipliers and continued by a third.  Same certified
+    optimum as the single pass, and both paths are actually taken."""
+    from biped_mpc_py_b200 import synth
+    from oracle import reference_mpc as rm
+    mpc, biped = rm.MPCParams(h=h), rm.BipedParams()
+    n = 384 if h == 10 else 48
+    b = synth.make_batch(n, shard_index=5, mpc=mpc, biped=biped, extend=(h != 10))
+    args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+    kw = dict(phase_k=b["phase_k"]) if h != 10 else {}
+    one = _run(lane_lib, mpc, biped, *args, **kw)
+    ipm_inline = int(np.median(one["iters"])) - 1   # about half of the robots are parked mid-way
+    lane_lib.lane_host_set_two_pass(1, ipm_inline)
+    try:
+        p0, q0 = lane_lib.lane_host_parked(), lane_lib.lane_host_parked_ipm()
+        two = _run(lane_lib, mpc, biped, *args, **kw)
+        parked, parked_ipm = lane_lib.lane_host_parked() - p0, lane_lib.lane_host_parked_ipm() - q0
+    finally:
+        lane_lib.lane_host_set_two_pass(0, 0)
+    assert parked >= n // 50, parked          # about one robot in eight needs a second polish round
+    assert parked_ipm >= n // 5, parked_ipm
+    assert (one["status"] == two["status"]).all() and (one["status"] == 0).mean() >= 0.9
+    ok = one["status"] == 0
+    # a robot continued from the float copy of its interior point may need one iteration more or less
+    assert np.abs(one["iters"] - two["iters"]).max() <= 2
+    scale = np.maximum(1.0, np.abs(one["controls"]).reshape(n, -1).max(axis=1))
+    assert (np.abs(one["controls"] - two["controls"]).reshape(n, -1).max(axis=1) / scale)[ok].max() <= 1e-8
+    assert np.abs(one["tau"] - two["tau"])[ok].max() <= 1e-7
+    assert (one["fric"] == two["fric"])[ok].all()

@@ -229,3 +229,41 @@ def test_handle_warm_start_in_a_caller_owned_loop():
     assert (outs[True][1][1:] == 0).mean() > 0.9           # later ticks: straight to the polish
     s.reset_warm_start()
     s.close()
+
+
+@pytest.mark.gpu
+def test_simulator_adapter_step_observe_loop_against_oracle():
+    """SimulatorAdapter (biped_mpc_py_b200/sim.py: the reference main script MPC.py:475-495 as a step/observe object) in a loop
+    with a CPU "simulator" - the oracle's plant step, joint angles held, feet by forward kinematics as MPC.py:478-479 - :
+    at every control period the adapter's controls and torques equal the oracle tick on the same observation, warm-started
+    or cold, and reset() restarts the clocks."""
+    import biped_mpc_py_b200 as bm
+    from biped_mpc_py_b200 import synth
+    from oracle import reference_mpc as rm
+    from oracle import rollout as ro
+    mpc, biped = bm.MPC(), synth.rollout_biped()
+    ompc, obiped = _params()
+    n, ticks = 3, 7
+    gait = np.array([1, 0, 1])
+    b = synth.make_batch(n, shard_index=21, mpc=mpc, biped=biped)
+    for warm in (True, False):
+        ctl = bm.SimulatorAdapter(n, mpc, biped, gait=gait, warm_start=warm, strict=True)
+        x = np.tile(rm.X_FB0, (n, 1)) + 0.02 * (b["x_fb"] - b["x_fb"].mean(axis=0))
+        q, qd = b["q"].copy(), 0.1 * b["qd"]
+        for k in range(ticks):
+            ctl.observe(x, q, qd)
+            tau = ctl.step()
+            assert (ctl.last["status"] == 0).all() and (ctl.tick == k + 1).all()
+            for i in range(n):
+                pf = rm.getFootPositionWorld(x[i], q[i], obiped).reshape(6)
+                np.testing.assert_allclose(ctl.last["pf_w"][i], pf, rtol=0, atol=1e-13)
+                want = ro.tick_once(x[i], pf, k, int(gait[i]), q[i], qd[i], ompc, obiped)
+                assert (ctl.last["contact"][i] == want["contact"]).all()
+                scale = max(1.0, np.abs(want["controls"]).max())
+                assert np.abs(ctl.last["controls"][i] - want["controls"]).max() / scale <= 1e-5, (warm, k, i)
+                assert np.abs(tau[i] - want["tau"]).max() <= 1e-4, (warm, k, i)
+            # the "simulator": the reference's own discretised model driven by the forces the controller asked for
+            x = np.stack([ro.srb_step(x[i], ctl.last["pf_w"][i], ctl.last["controls"][i][0], ompc, obiped) for i in range(n)])
+        ctl.reset()
+        assert (ctl.tick == 0).all()
+        ctl.close()

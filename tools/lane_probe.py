@@ -8,6 +8,10 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+if os.environ.get("EXP_LIB"):  # an experiment library built by tools/exp_build.sh
+    import biped_mpc_py_b200._lib as _l
+    _l.LIB_PATH = os.path.join(os.path.dirname(_l.LIB_PATH), "_exp", f"lib_{os.environ['EXP_LIB']}.so")
+    print("library:", _l.LIB_PATH, flush=True)
 from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
@@ -38,6 +42,12 @@ for cfg in cfgs:
         s.set_option("lane_ctas_per_sm", ctas)
         s.set_option("lane_sync", sync)
         s.set_option("lane_prefetch", pref)
+        if len(cfg) > 4:
+            s.set_option("polish_rounds", cfg[4])
+        if len(cfg) > 5:
+            s.set_option("lane_inline_rounds", cfg[5])
+        if len(cfg) > 6:
+            s.set_option("lane_ipm_inline", cfg[6])
     out = s.step(*d)
     torch.cuda.synchronize()
     ts = []
