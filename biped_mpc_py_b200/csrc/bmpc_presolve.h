@@ -40,7 +40,10 @@ inline int build_dev_params_impl(const bmpc_params& P, DevParams& d, std::string
     // one round at a time (h = 30 instances needing 5-7 rounds were measured with tools/kernel_model.py)
     d.polish_rounds = P.h > 10 ? 16 : 4;
     d.lock_mode = 3;        // loose lockstep of the robots of a CTA (bmpc_tick.cuh)
-    d.lane_prefetch = 1;
+    // bulk L2 prefetch of the next block record: off.  It paid while the lane kernels waited on latency; their first pass now moves
+    // 5.5 TB/s of its own workspace (85 % of the measured copy bandwidth) and the prefetch's unused elements only add to that:
+    // 28.2 ms per 262,144-robot tick without, 28.5 - 28.9 with (bmpc_set_option "lane_prefetch" turns it back on)
+    d.lane_prefetch = 0;
     d.lane_sync = 2;
     d.warm_rounds = 6;      // polish rounds allowed to a warm-started tick before it falls back to the cold path
     d.step_frac = 0.99;     // fraction of the step to the boundary (0.9 once an instance is past 14 iterations)
