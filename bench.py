@@ -20,8 +20,9 @@ for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
 # NCCL writes its debug output (communicator ranks, rings, NVLS) to STDOUT.  Rank 0 must print exactly one JSON line
 # there, so the process's fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved stdout:
 # NCCL_DEBUG=INFO stays visible (on stderr) for whoever wants to check the communicator.
-os.environ.setdefault("NCCL_DEBUG", "INFO")
-os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+# (Set, not defaulted: an inherited NCCL_DEBUG=WARN would hide the rank count the driver looks for.)
+os.environ["NCCL_DEBUG"] = "INFO"
+os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
 
 import argparse
 import json
