@@ -22,6 +22,9 @@ DEPS = [SRC] + [os.path.join(ROOT, "biped_mpc_py_b200", "csrc", f)
 
 @pytest.fixture(scope="module")
 def lane_lib():
+    # LANE_HOST_LIB: a pre-built variant of the library, e.g. the -fsanitize=address,undefined build of profiles/r2_sanitizer.txt
+    if os.environ.get("LANE_HOST_LIB"):
+        return ctypes.CDLL(os.environ["LANE_HOST_LIB"])
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
         if not os.path.exists(nvcc):

@@ -232,6 +232,39 @@ def test_handle_warm_start_in_a_caller_owned_loop():
 
 
 @pytest.mark.gpu
+def test_handle_warm_start_with_a_growing_batch():
+    """The warm-start store of a handle only describes the robots of the last call that went through: a call with MORE robots
+    must start cold (the store's tail was never written - it is initialised to "no guess" - and warm_n gates it), a call with
+    the same or fewer robots starts warm; results equal the cold solve either way."""
+    import torch
+    from biped_mpc_py_b200 import BatchedMPC, MPC, synth
+    n = 48
+    mpc, biped = MPC(), synth.rollout_biped()
+    b = synth.make_batch(n, shard_index=31, mpc=mpc, biped=biped)
+    keys = ("x_fb", "t", "foot", "contact", "q", "qd", "pf_w")
+    cold = BatchedMPC(mpc, biped, max_batch=n)
+    ref = cold.step_host(*[b[k] for k in keys])
+    cold.close()
+    s = BatchedMPC(mpc, biped, max_batch=n)
+    s.warm_start(True)
+    first = s.step_host(*[b[k][:16] for k in keys])          # cold (nothing stored), stores 16 robots
+    assert first["iters"].min() > 0
+    # warm: the same 16 robots from their own active sets shifted by one stage (these are unrelated random states, not a closed loop,
+    # so only some of the guesses certify; those robots skip the interior point: 0 iterations)
+    again = s.step_host(*[b[k][:16] for k in keys])
+    assert (again["iters"] == 0).any()
+    grown = s.step_host(*[b[k] for k in keys])               # 48 > 16: cold for everybody
+    assert grown["iters"].min() > 0
+    shrunk = s.step_host(*[b[k][:32] for k in keys])         # 32 <= 48: warm
+    assert (shrunk["iters"] == 0).any()
+    for out, m in ((first, 16), (again, 16), (grown, n), (shrunk, 32)):
+        assert (out["status"] == 0).all()
+        np.testing.assert_allclose(out["controls"], ref["controls"][:m], rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(out["tau"], ref["tau"][:m], rtol=1e-7, atol=1e-7)
+    s.close()
+
+
+@pytest.mark.gpu
 def test_simulator_adapter_step_observe_loop_against_oracle():
     """SimulatorAdapter (biped_mpc_py_b200/sim.py: the reference main script MPC.py:475-495 as a step/observe object) in a loop
     with a CPU "simulator" - the oracle's plant step, joint angles held, feet by forward kinematics as MPC.py:478-479 - :
