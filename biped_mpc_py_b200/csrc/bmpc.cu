@@ -100,6 +100,7 @@ struct bmpc_handle {
     int opt_lane_warps = -1;       // warps (32 robots each) per CTA
     int opt_lowlat = -1;           // 0 disables the 128-thread walking variant for batches <= 8
     int opt_lane_ipm_inline = -1;     // interior-point iterations of the first lane pass before a robot is parked (0: never)
+    int opt_lane_defer_cap = -1;      // size of the two park stores in robots (-1: a quarter of max_batch, at least 4,096)
     int opt_lane_defer_min = -1;      // smallest class that uses the second pass (-1: two waves of slices)
     int opt_lane_inline_rounds = -1;  // polish rounds of the first lane pass before a robot is parked for the second (0: one pass)
     Variant fallback;         // dense re-solve of instances the stage-wise class-1 kernel did not certify (h = 30), or empty
@@ -164,12 +165,13 @@ void free_lane(LaneVariant& v) {
     v.d_ws = nullptr, v.d_defer = nullptr, v.d_defer_list = nullptr, v.d_ipm = nullptr, v.d_ipm_list = nullptr;
 }
 
-int setup_lane(LaneVariant& v, const DevParams& d, int nf, int num_sms, int ctas_per_sm, int warps, int max_batch) {
+int setup_lane(LaneVariant& v, const DevParams& d, int nf, int num_sms, int ctas_per_sm, int warps, int max_batch, int cap_override) {
     const LaneKernelInfo k = d.h == 30 ? lane_kernel_info_h30(nf, lane_rowmask(d)) : lane_kernel_info_h10(nf, lane_rowmask(d));
     if (!k.fn) return fail("no lane kernel for this horizon");
     free_lane(v);
     v.defer_floats = k.defer_floats;
-    v.defer_cap = std::max(4096, ((max_batch + 3) / 4 + 31) / 32 * 32);  // a quarter of the batch can be parked for the polish (about one robot in eight is)
+    v.defer_cap = cap_override > 0 ? (cap_override + 31) / 32 * 32
+                                   : std::max(4096, ((max_batch + 3) / 4 + 31) / 32 * 32);  // a quarter of the batch can be parked for the polish (about one robot in eight is)
     v.ipm_floats = k.ipm_floats;
     v.ipm_cap = v.defer_cap;                                              // and for the interior point (about one robot in forty is)
     v.fn = k.fn;
@@ -366,10 +368,10 @@ int setup_lanes(bmpc_handle* h) {
     h->lane_min = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 1024 : 4096);
     h->lane[0].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 2048 : 8192);
     h->lane[1].min_count = h->opt_lane_min >= 0 ? h->opt_lane_min : (h30 ? 1024 : 4096);
-    int rc = setup_lane(h->lane[0], d, 1, h->num_sms, ctas, warps, h->max_batch);
+    int rc = setup_lane(h->lane[0], d, 1, h->num_sms, ctas, warps, h->max_batch, h->opt_lane_defer_cap);
     if (!rc && mode >= 2) {
         const int mc = h->lane[1].min_count;
-        rc = setup_lane(h->lane[1], d, 2, h->num_sms, ctas, warps, h->max_batch);
+        rc = setup_lane(h->lane[1], d, 2, h->num_sms, ctas, warps, h->max_batch, h->opt_lane_defer_cap);
         h->lane[1].min_count = mc;
     }
     return rc;
@@ -663,6 +665,7 @@ int bmpc_set_option(bmpc_handle* h, const char* name, int value) {
     else if (k == "lowlat") { h->opt_lowlat = value; return 0; }
     else if (k == "lane_inline_rounds") { h->opt_lane_inline_rounds = value; return 0; }
     else if (k == "lane_defer_min") { h->opt_lane_defer_min = value; return 0; }
+    else if (k == "lane_defer_cap") h->opt_lane_defer_cap = value;
     else if (k == "lane_ipm_inline") { h->opt_lane_ipm_inline = value; return 0; }
     else if (k == "lane_prefetch") { h->dp.lane_prefetch = value != 0; return 0; }
     else if (k == "lane_sync") { h->dp.lane_sync = value; return 0; }

@@ -155,6 +155,8 @@ int bmpc_debug_assemble(bmpc_handle* h,
  *   "lane_inline_rounds" polish rounds of the first pass before a robot that needs more is parked for the polish pass
  *                       (default 1; 0: no later passes at all)
  *   "lane_defer_min"    smallest class for which robots are parked (default: two waves of resident slices; -1 restores it)
+ *   "lane_defer_cap"    size of the two park stores in robots (default: a quarter of max_batch, at least 4,096); a robot that
+ *                       finds its store full carries on in the pass it is in
  *   "polish_rounds"     budget of polish rounds per attempt (default 4 at h = 10, 16 at h = 30)
  *   "lowlat"            0 disables the 128-thread low-latency kernel used for batches <= 8
  * With "lane_min" = 1, "lane_defer_min" = 1 and "lowlat" = 0 every robot takes the same code path whatever batch it

@@ -409,3 +409,27 @@ def test_kernel_family_across_the_size_gates_and_pinned(torch_cuda):
         # and the pinned families agree with the default dispatch to rounding
         dv = np.abs(whole["controls"] - whole_auto["controls"]).reshape(n, -1).max(axis=1) / scale
         assert dv.max() <= 1e-6, (family, dv.max())
+
+
+def test_lane_park_stores_overflow_gracefully(torch_cuda):
+    """The later passes of the lane kernels park stragglers in two stores of bounded size.  With stores far too small for the
+    batch (lane_defer_cap = 64 robots for ~1,000 stragglers) a robot that finds its store full carries on in the pass it is in:
+    every robot still ends certified, with the result of the default configuration."""
+    from biped_mpc_py_b200 import synth
+    n = 8192
+    mpc, biped = variant_params(0)
+    b = synth.make_batch(n, shard_index=17, mpc=mpc, biped=biped)
+    args = (b["x_fb"], b["t"], b["foot"], b["contact"], b["q"], b["qd"], b["pf_w"])
+    outs = {}
+    for cap in (-1, 64):
+        solver, _, _ = _solver(0, max_batch=n)
+        solver.pin_kernel_family("lane")          # parking on for every class size
+        solver.set_option("lane_defer_cap", cap)
+        outs[cap] = solver.step_host(*args)
+        solver.close()
+    for cap in (-1, 64):
+        assert (outs[cap]["status"] == 0).all(), np.bincount(outs[cap]["status"])
+    scale = np.maximum(1.0, np.abs(outs[-1]["controls"]).reshape(n, -1).max(axis=1))
+    du = np.abs(outs[64]["controls"] - outs[-1]["controls"]).reshape(n, -1).max(axis=1) / scale
+    assert du.max() <= 1e-8, du.max()
+    assert np.abs(outs[64]["iters"] - outs[-1]["iters"]).max() <= 2   # parked robots continue from the float copy of their interior point
