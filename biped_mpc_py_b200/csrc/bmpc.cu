@@ -97,6 +97,7 @@ struct bmpc_handle {
     int opt_lane_mode = -1;        // 2 both classes, 1 walking class only, 0 warp-per-robot kernels only
     int opt_lane_min = -1;         // overrides the three size gates
     int opt_lane_ctas_per_sm = -1; // resident CTAs per SM of the lane kernels
+    int opt_lane_ctas_standing = -1;  // ... of the standing class only (-1: as the walking class)
     int opt_lane_warps = -1;       // warps (32 robots each) per CTA
     int opt_lowlat = -1;           // 0 disables the 128-thread walking variant for batches <= 8
     int opt_lane_ipm_inline = -1;     // interior-point iterations of the first lane pass before a robot is parked (0: never)
@@ -371,7 +372,8 @@ int setup_lanes(bmpc_handle* h) {
     int rc = setup_lane(h->lane[0], d, 1, h->num_sms, ctas, warps, h->max_batch, h->opt_lane_defer_cap);
     if (!rc && mode >= 2) {
         const int mc = h->lane[1].min_count;
-        rc = setup_lane(h->lane[1], d, 2, h->num_sms, ctas, warps, h->max_batch, h->opt_lane_defer_cap);
+        rc = setup_lane(h->lane[1], d, 2, h->num_sms, h->opt_lane_ctas_standing > 0 ? h->opt_lane_ctas_standing : ctas, warps, h->max_batch,
+                        h->opt_lane_defer_cap);
         h->lane[1].min_count = mc;
     }
     return rc;
@@ -661,6 +663,7 @@ int bmpc_set_option(bmpc_handle* h, const char* name, int value) {
     if (k == "lane_mode") h->opt_lane_mode = value;
     else if (k == "lane_min") h->opt_lane_min = value;
     else if (k == "lane_ctas_per_sm") h->opt_lane_ctas_per_sm = value;
+    else if (k == "lane_ctas_standing") h->opt_lane_ctas_standing = value;
     else if (k == "lane_warps") h->opt_lane_warps = value;
     else if (k == "lowlat") { h->opt_lowlat = value; return 0; }
     else if (k == "lane_inline_rounds") { h->opt_lane_inline_rounds = value; return 0; }

@@ -146,6 +146,7 @@ int bmpc_debug_assemble(bmpc_handle* h,
  *                       below which a class stays on the warp-per-robot kernel); -1 restores the defaults
  *   "lane_ctas_per_sm"  resident CTAs per SM of the lane-per-robot kernels (0 / -1: as many as fit)
  *   "lane_warps"        warps (32 robots each) per CTA of the lane-per-robot kernels (default 4)
+ *   "lane_ctas_standing" resident CTAs per SM of the standing class's lane kernel only (measurement: co-residency of the classes)
  *   "lane_prefetch"     0 disables the bulk L2 prefetch of the lane-per-robot kernels (measurement only)
  *   "lane_sync"         lockstep of the warps of a lane-kernel CTA: 2 (default) barrier per stage of every sweep,
  *                       1 per iteration, 0 independent warps; + 4: the polish of every warp on its own; + 8: one barrier

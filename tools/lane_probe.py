@@ -48,6 +48,8 @@ for cfg in cfgs:
             s.set_option("lane_inline_rounds", cfg[5])
         if len(cfg) > 6:
             s.set_option("lane_ipm_inline", cfg[6])
+        if len(cfg) > 7:
+            s.set_option("lane_ctas_standing", cfg[7])
     out = s.step(*d)
     torch.cuda.synchronize()
     ts = []
