@@ -8,7 +8,7 @@ rm -rf $d; mkdir -p $d/biped_mpc_py_b200 $root/biped_mpc_py_b200/csrc/_exp
 cp -r $root/include $d/include
 mkdir -p $d/biped_mpc_py_b200/csrc && cp $root/biped_mpc_py_b200/csrc/*.cu $root/biped_mpc_py_b200/csrc/*.cuh $root/biped_mpc_py_b200/csrc/*.h $d/biped_mpc_py_b200/csrc/
 cd $d/biped_mpc_py_b200/csrc
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DBMPC_LANE_UNIT=10 -c -o lane_h10.o bmpc_lane.cu 2>&1 | grep -v deprecated || true
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DBMPC_LANE_UNIT=10 $EXP_FLAGS -c -o lane_h10.o bmpc_lane.cu 2>&1 | grep -v deprecated || true
 if [ "$2" = "all" ]; then
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -c -o bmpc.o bmpc.cu 2>&1 | grep -v deprecated || true
 else
