@@ -49,16 +49,26 @@ static void run_f(const DevParams& d, std::vector<double>& w, std::vector<double
 }
 template <int HZ, int NF, unsigned RM>
 static void run_rm(const DevParams& d, std::vector<double>& w, std::vector<double>& ps, const IoPtrs& io, int i, bool f32) {
+#ifdef LANE_HOST_MINIMAL  // (sanitizer build: only what the GPU runs - float factor storage)
+    (void)f32;
+    run_f<HZ, NF, true, RM>(d, w, ps, io, i);
+#else
     if (f32) run_f<HZ, NF, true, RM>(d, w, ps, io, i);
     else run_f<HZ, NF, false, RM>(d, w, ps, io, i);
+#endif
 }
 // same choice as bmpc_lane.cu: the instantiation specialised for the presolve's row set if there is one, else the generic one
 template <int HZ, int NF>
 static void run_one(const DevParams& d, std::vector<double>& w, std::vector<double>& ps, const IoPtrs& io, int i, bool f32) {
     const unsigned rm = lane_rowmask(d);
+#ifdef LANE_HOST_MINIMAL  // (sanitizer build: the reference's row set through its specialised instantiation, everything else generic)
+    if (rm == kRowsRef) run_rm<HZ, NF, kRowsRef>(d, w, ps, io, i, f32);
+    else run_rm<HZ, NF, 0u>(d, w, ps, io, i, f32);
+#else
     if (rm == kRowsRef) run_rm<HZ, NF, kRowsRef>(d, w, ps, io, i, f32);
     else if (rm == kRowsSym) run_rm<HZ, NF, kRowsSym>(d, w, ps, io, i, f32);
     else run_rm<HZ, NF, 0u>(d, w, ps, io, i, f32);
+#endif
 }
 
 // factor storage of the interior point: 1 = float (what the GPU kernels run), 0 = double (numerical reference for the tests)
