@@ -432,4 +432,5 @@ def test_lane_park_stores_overflow_gracefully(torch_cuda):
     scale = np.maximum(1.0, np.abs(outs[-1]["controls"]).reshape(n, -1).max(axis=1))
     du = np.abs(outs[64]["controls"] - outs[-1]["controls"]).reshape(n, -1).max(axis=1) / scale
     assert du.max() <= 1e-8, du.max()
-    assert np.abs(outs[64]["iters"] - outs[-1]["iters"]).max() <= 2   # parked robots continue from the float copy of their interior point
+    # (iteration counts are not compared: a robot that loses the race for the last place of a store is solved by the warp-per-robot
+    #  kernels, whose interior point has a Gondzio corrector and needs fewer iterations)
