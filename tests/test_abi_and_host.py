@@ -66,6 +66,9 @@ def test_no_gpu_means_loud_failure_not_fallback(lib):
     assert rc != 0 and b"no CUDA device" in lib.bmpc_last_error()
     with pytest.raises(RuntimeError):
         BatchedMPC(MPC(), Biped(), max_batch=4)
+    from biped_mpc_py_b200 import SimulatorAdapter
+    with pytest.raises(RuntimeError):      # the simulator adapter has no CPU path either
+        SimulatorAdapter(2, MPC(), Biped())
 
 
 def test_product_does_not_import_the_oracle():
@@ -96,3 +99,21 @@ def test_synthetic_workload_feet_match_the_oracle_kinematics():
     b = synth.make_batch(200, shard_index=3)
     want = np.stack([rm.getFootPositionWorld(b["x_fb"][i], b["q"][i], rm.BipedParams()).reshape(6) for i in range(200)])
     np.testing.assert_allclose(b["pf_w"], want, rtol=0, atol=1e-13)
+
+
+def test_simulator_adapter_clock_and_contact_rows_match_the_oracle_rule():
+    """The adapter's own clock (biped_mpc_py_b200/sim.py): integer ticks, gait phase = tick % 10, contact rows of the table at
+    MPC.py:52-55 - the rule R2 of oracle/rollout.py - checked without a GPU on the expression the adapter uses."""
+    from oracle import rollout as ro
+    import inspect
+    from biped_mpc_py_b200 import sim
+    src = inspect.getsource(sim.SimulatorAdapter.step)
+    assert "rows < period // 2" in src and "self.tick % period" in src   # the expression mirrored below
+    period, h = 10, 10
+    for tick in range(0, 25):
+        for gait in (0, 1):
+            phase = np.array([tick % period])
+            rows = (phase[:, None] + np.arange(h)[None, :]) % period
+            left = rows < period // 2
+            contact = np.where((np.array([gait]) == 1)[:, None, None], np.stack([left, ~left], axis=2), True).astype(np.uint8)[0]
+            assert (contact == ro.contact_rows(tick, gait, h)).all(), (tick, gait)
