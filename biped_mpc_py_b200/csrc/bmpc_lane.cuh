@@ -1528,7 +1528,7 @@ struct LaneSolver {
             if (pol && !changed) {
                 // dual check: minus the gradient must be a non-negative combination of the active rows
                 grad(L::o_u, L::o_tv, nullptr);
-                bool fail = false;
+                bool fail = false, released = false;
 #pragma unroll 1
                 for (int v = 0; v < S; ++v) {
                     SV r = rec(v);
@@ -1539,8 +1539,12 @@ struct LaneSolver {
                         // releasing several rows of many blocks at once can cycle (release, re-add as violated, release ...):
                         // after the first rounds only one row per block is released at a time
                         if (round > 3 && drop != 0u) drop &= (~drop + 1u);
+                        // ... and if that still cycles (several blocks exchanging the same pair of rows in step: seen on a degenerate
+                        // standing instance at h = 30, period five rounds), ONE release per round in the whole problem, lowest block
+                        // and lowest row first - the single exchange of a textbook active-set method (Bland's rule)
                         if (drop == 0u) fail = true;
-                        else r[L::o_am] = (double)(mk & ~drop), changed = true;
+                        else if (round > 8 && released) changed = true;
+                        else r[L::o_am] = (double)(mk & ~drop), changed = true, released = true;
 #ifdef BMPC_LANE_DEBUG
                         printf("[polish] round %d block %d mask 0x%x dual check: drop 0x%x gs %.3e\n", round, v, mk, drop, gs);
 #endif

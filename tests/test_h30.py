@@ -146,16 +146,18 @@ def test_h30_lane_per_robot_front_end_matches_warp_kernels():
     assert np.abs(out["tau"] - ref["tau"]).max() <= 1e-6
 
 
-def test_h30_nearly_degenerate_instance_is_certified():
-    """Regression (round-1 gap): instance 6464 of synthetic shard 1000 at h = 30 (standing) was returned uncertified (status 1)
-    by every kernel - its polish cycled between releasing and re-adding rows of ten blocks at once.  With the one-row-per-block
-    release rule and the last-resort pass it is certified and agrees with the oracle, inside a small batch (warp-per-robot
-    kernels first, then the last resort) and inside a batch that takes the lane-per-robot kernels."""
+@pytest.mark.parametrize("shard,i", [(1000, 6464), (1006, 61551)])
+def test_h30_nearly_degenerate_instance_is_certified(shard, i):
+    """Regression: two standing instances of the synthetic h = 30 workload that were returned uncertified (status 1) by every
+    kernel.  Shard 1000 / 6464 (round 1): the polish cycled between releasing and re-adding rows of ten blocks at once - fixed by
+    the one-row-per-block release rule and the last-resort pass.  Shard 1006 / 61551 (found by the 8-GPU bench of round 2): several
+    blocks exchanged the same pair of rows in step, period five rounds, for all 128 rounds of the last resort (0.4 s) - fixed by
+    the single exchange per round from round 9 on (Bland's rule).  Both are certified and agree with the oracle, inside a small
+    batch (warp-per-robot kernels first, then the last resort) and inside a batch that takes the lane-per-robot kernels."""
     from oracle import reference_mpc as rm
     from biped_mpc_py_b200 import BatchedMPC, MPC, Biped, synth
     mpc = MPC(h=30)
-    b = synth.make_batch(65536, shard_index=1000, mpc=mpc, extend=True)
-    i = 6464
+    b = synth.make_batch(65536, shard_index=shard, mpc=mpc, extend=True)
     _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], rm.MPCParams(h=30), rm.BipedParams(), b["contact"][i], extend=True)
     for lo, hi in ((i - 32, i + 32), (i - 2048, i + 2048)):
         s = BatchedMPC(mpc, Biped(), max_batch=hi - lo, extend_gait=True)

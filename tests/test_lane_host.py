@@ -186,3 +186,20 @@ def test_lane_solver_later_passes_match_one_pass(lane_lib, h):
     assert (np.abs(one["controls"] - two["controls"]).reshape(n, -1).max(axis=1) / scale)[ok].max() <= 1e-8
     assert np.abs(one["tau"] - two["tau"])[ok].max() <= 1e-7
     assert (one["fric"] == two["fric"])[ok].all()
+
+
+def test_lane_solver_h30_cycling_instance_is_certified(lane_lib):
+    """A degenerate standing instance at h = 30 (synthetic shard 1006, index 61551) whose polish cycled - several blocks exchanging
+    the same pair of rows in step - until the single-exchange rule (one release per round in the whole problem from round 9 on): the
+    lane solver certifies it within its round budget and agrees with the oracle."""
+    from biped_mpc_py_b200 import synth
+    from oracle import reference_mpc as rm
+    mpc, biped = rm.MPCParams(h=30), rm.BipedParams()
+    b = synth.make_batch(65536, shard_index=1006, mpc=mpc, biped=biped, extend=True)
+    i = 61551
+    sl = slice(i, i + 1)
+    out = _run(lane_lib, mpc, biped, b["x_fb"][sl], b["t"][sl], b["foot"][sl], b["contact"][sl], b["q"][sl], b["qd"][sl], b["pf_w"][sl],
+               phase_k=b["phase_k"][sl])
+    assert out["status"][0] == 0
+    _, u = rm.solve_mpc(b["x_fb"][i], float(b["t"][i]), b["foot"][i], mpc, biped, b["contact"][i], extend=True)
+    assert np.abs(out["controls"][0] - u).max() / max(1.0, np.abs(u).max()) <= 1e-5
