@@ -1540,10 +1540,12 @@ struct LaneSolver {
                         // after the first rounds only one row per block is released at a time
                         if (round > 3 && drop != 0u) drop &= (~drop + 1u);
                         // ... and if that still cycles (several blocks exchanging the same pair of rows in step: seen on a degenerate
-                        // standing instance at h = 30, period five rounds), ONE release per round in the whole problem, lowest block
-                        // and lowest row first - the single exchange of a textbook active-set method (Bland's rule)
+                        // standing instance at h = 30, period five rounds), from round 33 on ONE release per round in the whole
+                        // problem, lowest block and lowest row first - the single exchange of a textbook active-set method (Bland's
+                        // rule).  Not earlier: an instance that has to release rows in many blocks (the other degenerate h = 30
+                        // instance: 31 rounds) would take a round per row (70 rounds with the rule from round 9 on).
                         if (drop == 0u) fail = true;
-                        else if (round > 8 && released) changed = true;
+                        else if (round > 32 && released) changed = true;
                         else r[L::o_am] = (double)(mk & ~drop), changed = true, released = true;
 #ifdef BMPC_LANE_DEBUG
                         printf("[polish] round %d block %d mask 0x%x dual check: drop 0x%x gs %.3e\n", round, v, mk, drop, gs);
